@@ -1,0 +1,65 @@
+"""ctypes binding of libpaintmind_b200.so (the C-ABI in include/paintmind_b200.h).
+
+The product path has NO fallback: if the shared library is missing, or a call returns non-zero,
+a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpaintmind_b200.so"
+_lib = None
+
+PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH = 0, 1, 2
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("out", C.c_void_p),
+        ("bias", C.c_void_p), ("colsum", C.c_void_p), ("stats", C.c_void_p),
+        ("pos", C.c_void_p), ("res", C.c_void_p),
+        ("lda", C.c_int64), ("ldw", C.c_int64), ("ld_out", C.c_int64),
+        ("ld_pos", C.c_int64), ("ld_res", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("pos_rows", C.c_int32), ("out_mode", C.c_int32), ("swiglu", C.c_int32), ("bn", C.c_int32),
+        ("patch", C.c_int32), ("channels", C.c_int32), ("grid", C.c_int32), ("max_ctas", C.c_int32),
+    ]
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: build it with `python -m paintmind_b200.build` "
+            "(there is no CPU / PyTorch fallback for the hot path)")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.pm_version.restype = C.c_int
+    lib.pm_device_check.restype = C.c_int
+    lib.pm_error_string.restype = C.c_char_p
+    lib.pm_error_string.argtypes = [C.c_int]
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"libpaintmind_b200.so does not export {name}")
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+# every compute entry point declared in include/paintmind_b200.h
+EXPORTS = [
+    "pm_gemm_bf16",
+]
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pm_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: rc={rc} ({msg})")
