@@ -75,6 +75,75 @@ typedef struct pm_gemm_args {
 
 int pm_gemm_bf16(const pm_gemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head attention core, head_dim 64:  O[b, n, h*64:(h+1)*64] = softmax(scale * Q K^T) V.
+ * Replaces modules/attention.py:51-58 (CrossAttention) == :84-106 (MemoryEfficientCrossAttention,
+ * i.e. xformers.ops.memory_efficient_attention): self-attention (Nq == Nk) and cross-attention on
+ * the text context (Nk = 77, no mask — SURVEY.md N6).  Q/K/V/O are bf16, token-major, with head h
+ * at columns [h*64, h*64+64) from the given base pointer; ld* = row pitch, bs* = batch stride
+ * (elements).  The (b h) n d rearrange of the reference is done by TMA addressing.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pm_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int64_t ldq, ldk, ldv, ldo;
+  int64_t bsq, bsk, bsv, bso;
+  int32_t B, H, Nq, Nk, head_dim; /* head_dim must be 64 */
+  float scale;                     /* dim_head ** -0.5 (attention.py:31) */
+} pm_attn_args;
+
+int pm_attn_fwd(const pm_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Vector quantizer (stage1/quantize.py), e_dim = 32.
+ *   pm_vq_codebook_prep : en = l2norm(E) fp32 [n_e,32]; packed = bf16 [n_e,64] = [hi | lo] of en
+ *                         (quantize.py:21 — the reference re-normalises E on every forward)
+ *   pm_vq_fwd           : VectorQuantizer.forward (quantize.py:18-38): idx = argmin distance
+ *                         (first index on ties), zq = zn + (l2norm(E[idx]) - zn), *sse += sum of
+ *                         squared differences (loss = (1+beta) * sse / (M*32), quantize.py:33),
+ *                         hist[idx] += 1 (codebook usage; new in this build).
+ *                         cand_val/cand_idx: scratch [8, M] used when the codebook is split over
+ *                         several CTAs per row tile (small M); splits = 0 lets the library choose.
+ *   pm_vq_gather        : VectorQuantizer.decode_from_indice (quantize.py:40-44) when normalize=1;
+ *                         Pipeline.ids2tokens raw-table gather (generate.py:148-157) when 0.
+ *   pm_split_rows32     : fp32 [M,32] -> bf16 [M,64] = [hi | lo], the exact two-term operand the
+ *                         post_quant / token_proj GEMMs consume (K = 64 against [W | W]).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pm_vq_args {
+  const float* z;        /* [M, 32] raw latents, row pitch ldz                                 */
+  const float* en;       /* [n_e, 32] from pm_vq_codebook_prep                                 */
+  const void* packed;    /* [n_e, 64] bf16 from pm_vq_codebook_prep                            */
+  float* cand_val;       /* [8, M] scratch or NULL (then splits must be 1)                     */
+  int32_t* cand_idx;     /* [8, M] scratch or NULL                                             */
+  int64_t* idx;          /* [M] out                                                            */
+  float* zq;             /* [M, 32] out or NULL                                                */
+  void* zq_split;        /* [M, 64] bf16 out or NULL                                           */
+  double* sse;           /* accumulated (caller zeroes) or NULL                                */
+  uint64_t* hist;        /* [n_e] accumulated or NULL                                          */
+  int64_t ldz;
+  int32_t M, n_e, e_dim, splits;
+} pm_vq_args;
+
+int pm_vq_codebook_prep(const float* E, int32_t n_e, int32_t e_dim, float* en, void* packed, void* stream);
+int pm_vq_fwd(const pm_vq_args* args, void* stream);
+int pm_vq_gather(const int64_t* idx, int32_t M, int32_t n_rows, int32_t e_dim, const float* table,
+                 int32_t normalize, float* out, void* out_split, void* stream);
+int pm_split_rows32(const float* src, int64_t ld, int32_t M, void* out_split, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HBM-bound row kernels.
+ *   pm_patchify8 : im2col of the stride-8 patch conv (stage1/layers.py:82-83): fp32 NCHW image ->
+ *                  bf16 [B*(H/8)*(W/8), C*64], K order (c, kh, kw) = flattened Conv2d weight.
+ *   pm_layernorm : nn.LayerNorm over bf16 rows (layers.py:49,51,89,128; eps 1e-5).
+ *                  y == NULL: only stats[row] = (mean, rstd) (feeds the LN-folded GEMM epilogue);
+ *                  y != NULL: y = LN(x) * gamma + beta (bf16) and, if stats != NULL, the stats of y.
+ * ------------------------------------------------------------------------------------------- */
+int pm_patchify8(const float* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+int pm_layernorm(const void* x, int64_t ldx, int32_t M, int32_t D, float eps, const float* gamma,
+                 const float* beta, void* y, int64_t ldy, float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

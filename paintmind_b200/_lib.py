@@ -27,6 +27,27 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+        ("bsq", C.c_int64), ("bsk", C.c_int64), ("bsv", C.c_int64), ("bso", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float),
+    ]
+
+
+class VqArgs(C.Structure):
+    _fields_ = [
+        ("z", C.c_void_p), ("en", C.c_void_p), ("packed", C.c_void_p),
+        ("cand_val", C.c_void_p), ("cand_idx", C.c_void_p),
+        ("idx", C.c_void_p), ("zq", C.c_void_p), ("zq_split", C.c_void_p),
+        ("sse", C.c_void_p), ("hist", C.c_void_p),
+        ("ldz", C.c_int64),
+        ("M", C.c_int32), ("n_e", C.c_int32), ("e_dim", C.c_int32), ("splits", C.c_int32),
+    ]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -45,18 +66,28 @@ def load():
     lib.pm_device_check.restype = C.c_int
     lib.pm_error_string.restype = C.c_char_p
     lib.pm_error_string.argtypes = [C.c_int]
-    for name in EXPORTS:
+    for name, argtypes in EXPORTS.items():
         if not hasattr(lib, name):
             raise RuntimeError(f"libpaintmind_b200.so does not export {name}")
-        getattr(lib, name).restype = C.c_int
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
     _lib = lib
     return lib
 
 
-# every compute entry point declared in include/paintmind_b200.h
-EXPORTS = [
-    "pm_gemm_bf16",
-]
+# every compute entry point declared in include/paintmind_b200.h, with its C signature
+_p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+EXPORTS = {
+    "pm_gemm_bf16": [C.POINTER(GemmArgs), _p],
+    "pm_attn_fwd": [C.POINTER(AttnArgs), _p],
+    "pm_vq_codebook_prep": [_p, _i32, _i32, _p, _p, _p],
+    "pm_vq_fwd": [C.POINTER(VqArgs), _p],
+    "pm_vq_gather": [_p, _i32, _i32, _i32, _p, _i32, _p, _p, _p],
+    "pm_split_rows32": [_p, _i64, _i32, _p, _p],
+    "pm_patchify8": [_p, _p, _i32, _i32, _i32, _i32, _p],
+    "pm_layernorm": [_p, _i64, _i32, _i32, _f, _p, _p, _p, _i64, _p, _p],
+}
 
 
 def check(rc: int, what: str) -> None:

@@ -1,0 +1,85 @@
+"""Model configurations — same public names and values as the reference's paintmind/config.py
+(Config :4-37, vit_s_vqgan_config :40-66, pipeline_v1_config :68-77, ver2cfg :79-82), because
+every tensor shape on the hot path is defined here."""
+from __future__ import annotations
+
+import copy
+import json
+
+
+class Config:
+    """Attribute bag over a plain dict (dict <-> JSON), mirroring reference Config's surface:
+    to_dict / to_json / to_json_string / from_dict / from_json / clear."""
+
+    def __init__(self, config=None):
+        if config is not None:
+            self.from_dict(config)
+
+    def to_dict(self):
+        return copy.deepcopy(vars(self))
+
+    def to_json_string(self):
+        return json.dumps(self.to_dict(), indent=2)
+
+    def to_json(self, path):
+        with open(path, "w") as fh:
+            fh.write(self.to_json_string())
+
+    def from_dict(self, dct):
+        self.clear()
+        vars(self).update(dct)
+        return self.to_dict()
+
+    def from_json(self, json_path):
+        with open(json_path) as fh:
+            return self.from_dict(json.load(fh))
+
+    def clear(self):
+        vars(self).clear()
+
+    def __repr__(self):
+        return self.to_json_string()
+
+
+def _vit(image_size, patch_size, dim, depth, num_head, mlp_dim, dim_head, dropout, **io):
+    d = dict(image_size=image_size, patch_size=patch_size, dim=dim, depth=depth, num_head=num_head,
+             mlp_dim=mlp_dim)
+    d.update(io)
+    d.update(dim_head=dim_head, dropout=dropout)
+    return d
+
+
+vit_s_vqgan_config = {
+    "n_embed": 8192,
+    "embed_dim": 32,
+    "beta": 0.25,
+    "enc": _vit(256, 8, 512, 8, 8, 2048, 64, 0.0, in_channels=3),
+    "dec": _vit(256, 8, 512, 8, 8, 2048, 64, 0.0, out_channels=3),
+}
+
+pipeline_v1_config = {
+    "stage1": "vit-s-vqgan",
+    "t5": "t5-l",
+    "dim": 1024,
+    "dim_head": 64,
+    "mlp_dim": 4096,
+    "num_head": 16,
+    "depth": 12,
+    "dropout": 0.1,
+}
+
+# Small configurations used by the parity tests (not present in the reference registry; the
+# reference classes accept them unchanged because every size is a constructor argument).
+vit_tiny_test_config = {
+    "n_embed": 512,
+    "embed_dim": 32,
+    "beta": 0.25,
+    "enc": _vit(64, 8, 128, 2, 2, 256, 64, 0.0, in_channels=3),
+    "dec": _vit(64, 8, 128, 2, 2, 256, 64, 0.0, out_channels=3),
+}
+
+ver2cfg = {
+    "vit-s-vqgan": vit_s_vqgan_config,
+    "paintmindv1": pipeline_v1_config,
+    "vit-tiny-test": vit_tiny_test_config,
+}

@@ -58,4 +58,54 @@ int pm_gemm_bf16(const pm_gemm_args* a, void* stream) {
   return pm_gemm_launch(p, bn, a->out_mode, a->swiglu, static_cast<cudaStream_t>(stream));
 }
 
+int pm_attn_fwd(const pm_attn_args* a, void* stream) {
+  if (a == nullptr) return PM_ERR_INVALID;
+  AttnParams p;
+  p.q = a->q; p.k = a->k; p.v = a->v; p.o = a->o;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ldo;
+  p.bsq = a->bsq; p.bsk = a->bsk; p.bsv = a->bsv; p.bso = a->bso;
+  p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.head_dim = a->head_dim;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  return pm_attn_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int pm_vq_codebook_prep(const float* E, int32_t n_e, int32_t e_dim, float* en, void* packed, void* stream) {
+  if (e_dim != 32) return PM_ERR_INVALID;
+  return pm_vq_codebook_prep_launch(E, n_e, en, packed, static_cast<cudaStream_t>(stream));
+}
+
+int pm_vq_fwd(const pm_vq_args* a, void* stream) {
+  if (a == nullptr) return PM_ERR_INVALID;
+  VqParams p;
+  p.z = a->z; p.ldz = a->ldz; p.M = a->M;
+  p.en = a->en; p.packed = a->packed; p.n_e = a->n_e; p.e_dim = a->e_dim;
+  p.splits = a->splits;
+  p.cand_val = a->cand_val; p.cand_idx = a->cand_idx;
+  p.idx = reinterpret_cast<long long*>(a->idx);
+  p.zq = a->zq; p.zq_split = a->zq_split; p.sse = a->sse;
+  p.hist = reinterpret_cast<unsigned long long*>(a->hist);
+  if (p.cand_val == nullptr || p.cand_idx == nullptr) p.splits = 1;
+  return pm_vq_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int pm_vq_gather(const int64_t* idx, int32_t M, int32_t n_rows, int32_t e_dim, const float* table,
+                 int32_t normalize, float* out, void* out_split, void* stream) {
+  if (e_dim != 32) return PM_ERR_INVALID;
+  return pm_vq_gather_launch(reinterpret_cast<const long long*>(idx), M, n_rows, table, normalize, out, out_split,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int pm_split_rows32(const float* src, int64_t ld, int32_t M, void* out_split, void* stream) {
+  return pm_split_rows32_launch(src, ld, M, out_split, static_cast<cudaStream_t>(stream));
+}
+
+int pm_patchify8(const float* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  return pm_patchify_launch(img, out, B, C, H, W, 8, static_cast<cudaStream_t>(stream));
+}
+
+int pm_layernorm(const void* x, int64_t ldx, int32_t M, int32_t D, float eps, const float* gamma,
+                 const float* beta, void* y, int64_t ldy, float* stats, void* stream) {
+  return pm_layernorm_launch(x, ldx, M, D, eps, gamma, beta, y, ldy, stats, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

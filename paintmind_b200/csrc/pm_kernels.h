@@ -23,7 +23,44 @@ struct GemmParams {
   int max_ctas;
 };
 
+struct AttnParams {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int64_t ldq, ldk, ldv, ldo;      // row pitch in elements
+  int64_t bsq, bsk, bsv, bso;      // batch stride in elements
+  int B, H, Nq, Nk, head_dim;
+  float scale_log2;                // softmax scale * log2(e)
+};
+
+struct VqParams {
+  const float* z;                  // [M, 32] raw latents (row pitch ldz)
+  int64_t ldz;
+  int M;
+  const float* en;                 // [n_e, 32] normalised codebook (fp32)
+  const void* packed;              // [n_e, 64] bf16 = [e_hi | e_lo]
+  int n_e, e_dim;
+  int splits;                      // 0 = auto
+  float* cand_val;                 // [splits, M] scratch (splits > 1)
+  int* cand_idx;
+  long long* idx;                  // [M] int64 out
+  float* zq;                       // [M, 32] fp32 out (straight-through forward value)
+  void* zq_split;                  // [M, 64] bf16 out = [hi | lo] (decoder GEMM operand), optional
+  double* sse;                     // += sum (z_q - zn)^2
+  unsigned long long* hist;        // [n_e] += usage counts, optional
+};
+
 int pm_num_sms();
+int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
+int pm_vq_codebook_prep_launch(const float* E, int n_e, float* en, void* packed, cudaStream_t stream);
+int pm_vq_launch(const VqParams& p, cudaStream_t stream);
+int pm_vq_gather_launch(const long long* idx, int M, int n_rows, const float* table, int normalize,
+                        float* out, void* out_split, cudaStream_t stream);
+int pm_split_rows32_launch(const float* src, int64_t ld, int M, void* out_split, cudaStream_t stream);
+int pm_patchify_launch(const float* img, void* out, int B, int C, int H, int W, int P, cudaStream_t stream);
+int pm_layernorm_launch(const void* x, int64_t ldx, int M, int D, float eps, const float* gamma,
+                        const float* beta, void* y, int64_t ldy, float* stats, cudaStream_t stream);
 int pm_gemm_launch(const GemmParams& p, int bn, int out_mode, int swiglu, cudaStream_t stream);
 
 }  // namespace pm

@@ -1,0 +1,166 @@
+// pm_rowops.cu — HBM-bound row kernels of the tokenizer path (sm_100a): patch extraction,
+// LayerNorm statistics / LayerNorm.  One warp per row, 16-byte vector accesses, fp32 math.
+#include "pm_common.cuh"
+#include "pm_kernels.h"
+
+namespace pm {
+
+// ----------------------------------------------------------------------------------------------
+// im2col for the stride-P patch conv (stage1/layers.py:82-83): img fp32 NCHW -> bf16 [B*gh*gw, C*P*P]
+// with K order (c, kh, kw), i.e. the flattened Conv2d weight layout.  P == 8.
+// thread = (b, c, y, tw): reads 8 contiguous floats (coalesced along the image row), writes 16 B.
+// ----------------------------------------------------------------------------------------------
+__global__ void patchify8_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                 int B, int C, int H, int W) {
+  const int gw = W >> 3, gh = H >> 3;
+  const long long total = static_cast<long long>(B) * C * H * gw;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int tw = static_cast<int>(t % gw);
+  long long r = t / gw;
+  const int y = static_cast<int>(r % H); r /= H;
+  const int c = static_cast<int>(r % C);
+  const int b = static_cast<int>(r / C);
+  const float* src = img + ((static_cast<size_t>(b) * C + c) * H + y) * W + tw * 8;
+  const float4 v0 = *reinterpret_cast<const float4*>(src);
+  const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+  uint4 o;
+  o.x = pack_bf16x2(v0.x, v0.y); o.y = pack_bf16x2(v0.z, v0.w);
+  o.z = pack_bf16x2(v1.x, v1.y); o.w = pack_bf16x2(v1.z, v1.w);
+  const int th = y >> 3, kh = y & 7;
+  const size_t row = (static_cast<size_t>(b) * gh + th) * gw + tw;
+  *reinterpret_cast<uint4*>(out + row * (static_cast<size_t>(C) * 64) + c * 64 + kh * 8) = o;
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm over rows of a bf16 [M, D] matrix (D % 8 == 0, D <= 2048), eps inside the sqrt,
+// biased variance — nn.LayerNorm semantics (stage1/layers.py:49,51,89,128).
+//   MODE 0: stats only  -> stats[row] = (mean, rstd)   (consumed by the LN-folded GEMM epilogue)
+//   MODE 1: y = (x - mean) * rstd * gamma + beta  (bf16), optionally also the stats of y
+// ----------------------------------------------------------------------------------------------
+constexpr int LN_MAX_VEC = 8;   // 8 x (32 lanes x 8 elts) = 2048 columns
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int D, float eps,
+                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, int64_t ldy, float* __restrict__ stats) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const __nv_bfloat16* xr = x + static_cast<size_t>(warp) * ldx;
+  const int nvec = D >> 3;                      // 16-byte vectors per row
+  float v[LN_MAX_VEC][8];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int vi = i * 32 + lane;
+    if (vi < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      v[i][0] = bf16lo_to_f32(u.x); v[i][1] = bf16hi_to_f32(u.x);
+      v[i][2] = bf16lo_to_f32(u.y); v[i][3] = bf16hi_to_f32(u.y);
+      v[i][4] = bf16lo_to_f32(u.z); v[i][5] = bf16hi_to_f32(u.z);
+      v[i][6] = bf16lo_to_f32(u.w); v[i][7] = bf16hi_to_f32(u.w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[i][k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(D);
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int vi = i * 32 + lane;
+    if (vi < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[i][k] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / static_cast<float>(D) + eps);
+  if (MODE == 0) {
+    if (lane == 0) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(warp)) = make_float2(mean, rstd);
+    return;
+  }
+  __nv_bfloat16* yr = y + static_cast<size_t>(warp) * ldy;
+  float ysum = 0.0f;
+  float yv[LN_MAX_VEC][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int vi = i * 32 + lane;
+    if (vi < nvec) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const float a0 = (v[i][k] - mean) * rstd * g[k] + bb[k];
+        const float a1 = (v[i][k + 1] - mean) * rstd * g[k + 1] + bb[k + 1];
+        pk[k >> 1] = pack_bf16x2(a0, a1);
+        // statistics of the ROUNDED output (what the next GEMM will actually read)
+        yv[i][k] = bf16lo_to_f32(pk[k >> 1]);
+        yv[i][k + 1] = bf16hi_to_f32(pk[k >> 1]);
+        ysum += yv[i][k] + yv[i][k + 1];
+      }
+      *reinterpret_cast<uint4*>(yr + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
+    const float ymean = ysum / static_cast<float>(D);
+    float ysq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = yv[i][k] - ymean;
+          ysq = fmaf(d, d, ysq);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ysq += __shfl_xor_sync(0xffffffffu, ysq, o);
+    if (lane == 0)
+      *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(warp)) = make_float2(ymean, rsqrtf(ysq / static_cast<float>(D) + eps));
+  }
+}
+
+int pm_patchify_launch(const float* img, void* out, int B, int C, int H, int W, int P, cudaStream_t stream) {
+  if (img == nullptr || out == nullptr || P != 8 || (H % 8) != 0 || (W % 8) != 0 || B <= 0 || C <= 0) return PM_ERR_INVALID;
+  const long long total = static_cast<long long>(B) * C * H * (W / 8);
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  patchify8_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, C, H, W);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int pm_layernorm_launch(const void* x, int64_t ldx, int M, int D, float eps, const float* gamma,
+                        const float* beta, void* y, int64_t ldy, float* stats, cudaStream_t stream) {
+  if (x == nullptr || M <= 0 || D <= 0 || (D % 8) != 0 || D > LN_MAX_VEC * 256 || (ldx % 8) != 0) return PM_ERR_INVALID;
+  const int threads = 256;                       // 8 rows per block
+  const int blocks = (M + 7) / 8;
+  if (y == nullptr) {
+    if (stats == nullptr) return PM_ERR_INVALID;
+    layernorm_kernel<0><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, D, eps,
+                                                        nullptr, nullptr, nullptr, 0, stats);
+  } else {
+    if (gamma == nullptr || beta == nullptr || (ldy % 8) != 0) return PM_ERR_INVALID;
+    layernorm_kernel<1><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, D, eps,
+                                                        gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), ldy, stats);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pm

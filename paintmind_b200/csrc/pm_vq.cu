@@ -1,0 +1,462 @@
+// pm_vq.cu — factorised, l2-normalised vector quantizer on tcgen05 (sm_100a), e_dim = 32.
+//
+// Replaces VectorQuantizer.forward / decode_from_indice (reference stage1/quantize.py:18-44):
+//     zn = l2norm(z);  en = l2norm(E);  d = |zn|^2 + |en|^2 - 2 zn.en^T;  idx = argmin_j d
+//     z_q = l2norm(E[idx]);  loss = (1 + beta) * mean((z_q - zn)^2);  out = zn + (z_q - zn)
+// Both operands are unit vectors, so argmin_j d == argmax_j zn.en (first index on ties, as
+// torch.argmin); the [M, n_e] distance matrix is never materialised.
+//
+// Exactness: the contraction runs on bf16 tensor cores with BOTH operands split into
+// hi + lo bf16 halves, and all four partial products accumulated in fp32 TMEM:
+//     A row (K = 128) = [ z_hi | z_hi | z_lo | z_lo ]     (two 128B-swizzled K slabs)
+//     B row (K = 64)  = [ e_hi | e_lo ]                   (ONE slab, reused for both A slabs)
+// which reproduces the fp32 dot product to ~1e-7 (bf16 x bf16 products are exact in fp32).
+//
+// vq_main_kernel: work item = (256-row tile, codebook split).  320 threads:
+//   warp 0 lane 0 : TMA producer — streams the packed codebook [n_e, 64] bf16 (1 MB for 8192
+//                   codes) through a 6-stage smem ring of 128-code tiles
+//   warp 1 lane 0 : MMA issuer   — 2 row halves x 8 k-steps of 128x128x16 per code tile into
+//                   double-buffered TMEM accumulators (4 x 128 columns)
+//   warps 2..9    : one thread per latent row: normalise z, write the split A tile into swizzled
+//                   smem, then drain the accumulators with a running (max, first index) pair.
+// With splits == 1 the same threads finish the row in place (gather, straight-through output,
+// squared-error and usage-histogram reduction); otherwise vq_finalize_kernel merges the splits.
+#include "pm_common.cuh"
+#include "pm_kernels.h"
+
+namespace pm {
+
+constexpr int VQ_D = 32;                 // e_dim
+constexpr int VQ_BM = 256;               // rows per work item (two UMMA M=128 halves)
+constexpr int VQ_BN = 128;               // codes per tile
+constexpr int VQ_BSTAGES = 6;
+constexpr int VQ_A_SLAB = 128 * 128;     // 16 KB: 128 rows x 64 bf16
+constexpr int VQ_B_BYTES = VQ_BN * 128;  // 16 KB
+constexpr int VQ_THREADS = 320;
+constexpr int VQ_SMEM_BYTES = 1024 + 4 * VQ_A_SLAB + VQ_BSTAGES * VQ_B_BYTES + 512;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// normalise one 32-d row held in registers: x / max(||x||, 1e-12)   (quantize.py:5-6)
+__device__ __forceinline__ void l2norm32(float (&x)[VQ_D]) {
+  float ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VQ_D; ++i) ss = fmaf(x[i], x[i], ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < VQ_D; ++i) x[i] *= inv;
+}
+
+__device__ __forceinline__ void load_row32(const float* __restrict__ src, float (&x)[VQ_D]) {
+#pragma unroll
+  for (int i = 0; i < VQ_D; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(src + i);
+    x[i] = t.x; x[i + 1] = t.y; x[i + 2] = t.z; x[i + 3] = t.w;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// codebook prep: en = l2norm(E) (fp32) and the packed tensor-core operand [e_hi | e_lo] (bf16)
+// (the reference re-normalises the whole codebook on every forward, quantize.py:21)
+// ----------------------------------------------------------------------------------------------
+__global__ void vq_codebook_prep_kernel(const float* __restrict__ E, int n_e, float* __restrict__ en,
+                                        __nv_bfloat16* __restrict__ packed) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_e) return;
+  float x[VQ_D];
+  load_row32(E + static_cast<size_t>(j) * VQ_D, x);
+  l2norm32(x);
+#pragma unroll
+  for (int i = 0; i < VQ_D; i += 4)
+    *reinterpret_cast<float4*>(en + static_cast<size_t>(j) * VQ_D + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < VQ_D; i += 2) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[i]), h1 = __float2bfloat16_rn(x[i + 1]);
+    hi[i >> 1] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+    lo[i >> 1] = pack_bf16x2(x[i] - __bfloat162float(h0), x[i + 1] - __bfloat162float(h1));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(packed + static_cast<size_t>(j) * 64);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dst[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dst[4 + c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// per-row finish: gather, straight-through value, loss / histogram partials  (quantize.py:29-36)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float vq_finish_row(const VqParams& p, int row, int idx) {
+  float zn[VQ_D], e[VQ_D];
+  load_row32(p.z + static_cast<size_t>(row) * p.ldz, zn);
+  l2norm32(zn);
+  load_row32(p.en + static_cast<size_t>(idx) * VQ_D, e);   // == l2norm(E[idx])
+  float sse = 0.0f;
+  float out[VQ_D];
+#pragma unroll
+  for (int i = 0; i < VQ_D; ++i) {
+    const float d = e[i] - zn[i];
+    sse = fmaf(d, d, sse);
+    out[i] = zn[i] + d;                                     // z + (z_q - z).detach(), forward value
+  }
+  if (p.zq != nullptr) {
+    float* dst = p.zq + static_cast<size_t>(row) * VQ_D;
+#pragma unroll
+    for (int i = 0; i < VQ_D; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
+  }
+  if (p.zq_split != nullptr) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < VQ_D; i += 2) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(out[i]), h1 = __float2bfloat16_rn(out[i + 1]);
+      hi[i >> 1] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+      lo[i >> 1] = pack_bf16x2(out[i] - __bfloat162float(h0), out[i + 1] - __bfloat162float(h1));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.zq_split) + static_cast<size_t>(row) * 64);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[4 + c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+  }
+  if (p.idx != nullptr) p.idx[row] = static_cast<long long>(idx);
+  if (p.hist != nullptr) atomicAdd(p.hist + idx, 1ull);
+  return sse;
+}
+
+__global__ void __launch_bounds__(VQ_THREADS, 1)
+vq_main_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                                 // [rowhalf 2][slab 2][16 KB]
+  uint8_t* smB = smem + 4 * VQ_A_SLAB;                 // [VQ_BSTAGES][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + VQ_BSTAGES * VQ_B_BYTES);
+  uint64_t* b_full = bars;                             // [VQ_BSTAGES]
+  uint64_t* b_empty = bars + VQ_BSTAGES;               // [VQ_BSTAGES]
+  uint64_t* t_full = bars + 2 * VQ_BSTAGES;            // [2]
+  uint64_t* t_empty = t_full + 2;                      // [2]
+  uint64_t* a_full = t_empty + 2;                      // [1]  A tile written (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int row_tiles = (p.M + VQ_BM - 1) / VQ_BM;
+  const int items = row_tiles * p.splits;
+  const int codes_per_split = p.n_e / p.splits;        // host guarantees divisibility by VQ_BN... or tail masked
+  const int ntiles = (codes_per_split + VQ_BN - 1) / VQ_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < VQ_BSTAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 8);       // one arrival per drain warp
+    }
+    mbar_init(a_full, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int code0 = split * codes_per_split;
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(&b_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&b_full[st], VQ_B_BYTES);
+          tma_load_2d(smB + st * VQ_B_BYTES, &tmB, &b_full[st], 0, code0 + t * VQ_BN);
+          if (++st == VQ_BSTAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, VQ_BN, 0, 0);
+      int st = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      uint32_t item_ph = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        mbar_wait(a_full, item_ph);          // A tile of this item is in smem
+        item_ph ^= 1;
+        tc_fence_after();
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(&t_empty[as], aph ^ 1);
+          mbar_wait(&b_full[st], ph);
+          tc_fence_after();
+          const uint64_t db = umma_desc_sw128(smem_u32(smB + st * VQ_B_BYTES));
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const uint32_t tacc = tmem_base + (as * 2 + rh) * VQ_BN;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              // A k-step k: slab k/4 (z_hi|z_hi , z_lo|z_lo), 32 B step inside; B: [e_hi|e_lo] k%4
+              const uint64_t da = umma_desc_sw128(smem_u32(smA + (rh * 2 + (k >> 2)) * VQ_A_SLAB)) + 2 * (k & 3);
+              umma_ss(tacc, da, db + 2 * (k & 3), idesc, k != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&b_empty[st]);
+          umma_commit(&t_full[as]);
+          if (++st == VQ_BSTAGES) { st = 0; ph ^= 1; }
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int rh = (warp - 2) >> 2;                    // row half 0/1
+    const int r_in_half = q * 32 + lane;               // 0..127
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    int as = 0;
+    uint32_t aph = 0;
+    double sse_acc = 0.0;
+
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int rt = item / p.splits, split = item % p.splits;
+      const int row = rt * VQ_BM + rh * 128 + r_in_half;
+      const bool row_ok = row < p.M;
+      const int code0 = split * codes_per_split;
+
+      // ---- A tile: normalise, split hi/lo, write [hi|hi] / [lo|lo] into the swizzled slabs ----
+      // (all MMAs of the previous item have completed: its last t_full was waited on below)
+      {
+        float x[VQ_D];
+        if (row_ok) {
+          load_row32(p.z + static_cast<size_t>(row) * p.ldz, x);
+          l2norm32(x);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VQ_D; ++i) x[i] = 0.0f;
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < VQ_D; i += 2) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x[i]), h1 = __float2bfloat16_rn(x[i + 1]);
+          hi[i >> 1] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+          lo[i >> 1] = pack_bf16x2(x[i] - __bfloat162float(h0), x[i + 1] - __bfloat162float(h1));
+        }
+        uint8_t* a_hi = smA + (rh * 2 + 0) * VQ_A_SLAB + r_in_half * 128;
+        uint8_t* a_lo = smA + (rh * 2 + 1) * VQ_A_SLAB + r_in_half * 128;
+        const int sw = r_in_half & 7;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int s = (c & 3) * 4;
+          *reinterpret_cast<uint4*>(a_hi + ((c ^ sw) << 4)) = make_uint4(hi[s], hi[s + 1], hi[s + 2], hi[s + 3]);
+          *reinterpret_cast<uint4*>(a_lo + ((c ^ sw) << 4)) = make_uint4(lo[s], lo[s + 1], lo[s + 2], lo[s + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+      }
+
+      // ---- drain: running (max, first index) over this split's codes ----
+      float best = -INFINITY;
+      int bidx = code0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&t_full[as], aph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + lane_off + (as * 2 + rh) * VQ_BN;
+        const int cbase = code0 + t * VQ_BN;
+        const bool tail = (cbase + VQ_BN > code0 + codes_per_split) || (cbase + VQ_BN > p.n_e);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld_x32(tacc + cc * 32, r);
+          tmem_ld_wait();
+          if (cc == 3) {
+            // last TMEM read of this accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[as]);
+          }
+          if (!tail) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(r[i]);
+              const bool gt = v > best;
+              best = gt ? v : best;
+              bidx = gt ? (cbase + cc * 32 + i) : bidx;
+            }
+          } else {
+            const int lim = min(code0 + codes_per_split, p.n_e);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int code = cbase + cc * 32 + i;
+              const float v = __uint_as_float(r[i]);
+              const bool gt = (v > best) && (code < lim);
+              best = gt ? v : best;
+              bidx = gt ? code : bidx;
+            }
+          }
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+
+      if (p.splits == 1) {
+        float sse = 0.0f;
+        if (row_ok) sse = vq_finish_row(p, row, bidx);
+        sse_acc += static_cast<double>(warp_sum(sse));
+      } else if (row_ok) {
+        p.cand_val[static_cast<size_t>(split) * p.M + row] = best;
+        p.cand_idx[static_cast<size_t>(split) * p.M + row] = bidx;
+      }
+    }
+    if (p.splits == 1 && lane == 0 && p.sse != nullptr && sse_acc != 0.0) atomicAdd(p.sse, sse_acc);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// merge the per-split candidates (max value, ties -> lower index) and finish the rows
+__global__ void vq_finalize_kernel(const VqParams p) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  float sse = 0.0f;
+  if (row < p.M) {
+    float best = p.cand_val[row];
+    int bidx = p.cand_idx[row];
+    for (int s = 1; s < p.splits; ++s) {
+      const float v = p.cand_val[static_cast<size_t>(s) * p.M + row];
+      const int i = p.cand_idx[static_cast<size_t>(s) * p.M + row];
+      if (v > best || (v == best && i < bidx)) { best = v; bidx = i; }
+    }
+    sse = vq_finish_row(p, row, bidx);
+  }
+  sse = warp_sum(sse);
+  if ((threadIdx.x & 31) == 0 && p.sse != nullptr && sse != 0.0f) atomicAdd(p.sse, static_cast<double>(sse));
+}
+
+// decode_from_indice (quantize.py:40-44): z_q = l2norm(E[idx]); also the bf16 hi/lo split
+__global__ void vq_gather_kernel(const long long* __restrict__ idx, int M, int n_rows_table,
+                                 const float* __restrict__ table, int normalize,
+                                 float* __restrict__ out, __nv_bfloat16* __restrict__ out_split) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  long long i = idx[row];
+  if (i < 0) i = 0;
+  if (i >= n_rows_table) i = n_rows_table - 1;
+  float x[VQ_D];
+  load_row32(table + static_cast<size_t>(i) * VQ_D, x);
+  if (normalize) l2norm32(x);
+  if (out != nullptr) {
+#pragma unroll
+    for (int k = 0; k < VQ_D; k += 4)
+      *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * VQ_D + k) = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
+  }
+  if (out_split != nullptr) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int k = 0; k < VQ_D; k += 2) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x[k]), h1 = __float2bfloat16_rn(x[k + 1]);
+      hi[k >> 1] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+      lo[k >> 1] = pack_bf16x2(x[k] - __bfloat162float(h0), x[k + 1] - __bfloat162float(h1));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out_split + static_cast<size_t>(row) * 64);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[4 + c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+  }
+}
+
+// fp32 [M, 32] -> bf16 [M, 64] = [hi | lo]  (decoder input when the caller passes its own z)
+__global__ void split_rows32_kernel(const float* __restrict__ src, int64_t ld, int M, __nv_bfloat16* __restrict__ out_split) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float x[VQ_D];
+  load_row32(src + static_cast<size_t>(row) * ld, x);
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int k = 0; k < VQ_D; k += 2) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[k]), h1 = __float2bfloat16_rn(x[k + 1]);
+    hi[k >> 1] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+    lo[k >> 1] = pack_bf16x2(x[k] - __bfloat162float(h0), x[k + 1] - __bfloat162float(h1));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out_split + static_cast<size_t>(row) * 64);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dst[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dst[4 + c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// host launchers
+// ----------------------------------------------------------------------------------------------
+int pm_vq_codebook_prep_launch(const float* E, int n_e, float* en, void* packed, cudaStream_t stream) {
+  if (E == nullptr || en == nullptr || packed == nullptr || n_e <= 0) return PM_ERR_INVALID;
+  vq_codebook_prep_kernel<<<(n_e + 127) / 128, 128, 0, stream>>>(E, n_e, en, reinterpret_cast<__nv_bfloat16*>(packed));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int pm_vq_launch(const VqParams& p_in, cudaStream_t stream) {
+  VqParams p = p_in;
+  if (p.z == nullptr || p.en == nullptr || p.packed == nullptr || p.M <= 0 || p.n_e <= 0) return PM_ERR_INVALID;
+  if (p.e_dim != VQ_D || (p.ldz % 4) != 0) return PM_ERR_INVALID;
+  if (p.splits <= 0) {
+    // enough work items to fill the machine ~4x over, while keeping >= 8 code tiles per split
+    const int row_tiles = (p.M + VQ_BM - 1) / VQ_BM;
+    int s = 1;
+    while (row_tiles * s < 4 * pm_num_sms() && (p.n_e / (s * 2)) >= 8 * VQ_BN && (p.n_e % (s * 2 * VQ_BN)) == 0 && s < 8) s *= 2;
+    p.splits = s;
+  }
+  if (p.n_e % p.splits != 0) return PM_ERR_INVALID;
+  if (p.splits > 1 && ((p.n_e / p.splits) % VQ_BN != 0 || p.cand_val == nullptr || p.cand_idx == nullptr)) return PM_ERR_INVALID;
+  CUtensorMap tmB;
+  int rc = pm_make_tmap_2d(&tmB, p.packed, 2, p.n_e, 64, 64, VQ_BN, 64);
+  if (rc != PM_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vq_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  const int items = ((p.M + VQ_BM - 1) / VQ_BM) * p.splits;
+  const int grid = items < pm_num_sms() ? items : pm_num_sms();
+  vq_main_kernel<<<grid, VQ_THREADS, VQ_SMEM_BYTES, stream>>>(tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (p.splits > 1) {
+    vq_finalize_kernel<<<(p.M + 127) / 128, 128, 0, stream>>>(p);
+    e = cudaGetLastError();
+  }
+  return static_cast<int>(e);
+}
+
+int pm_vq_gather_launch(const long long* idx, int M, int n_rows, const float* table, int normalize,
+                        float* out, void* out_split, cudaStream_t stream) {
+  if (idx == nullptr || table == nullptr || M <= 0 || n_rows <= 0) return PM_ERR_INVALID;
+  vq_gather_kernel<<<(M + 127) / 128, 128, 0, stream>>>(idx, M, n_rows, table, normalize, out,
+                                                          reinterpret_cast<__nv_bfloat16*>(out_split));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int pm_split_rows32_launch(const float* src, int64_t ld, int M, void* out_split, cudaStream_t stream) {
+  if (src == nullptr || out_split == nullptr || M <= 0 || (ld % 4) != 0) return PM_ERR_INVALID;
+  split_rows32_kernel<<<(M + 127) / 128, 128, 0, stream>>>(src, ld, M, reinterpret_cast<__nv_bfloat16*>(out_split));
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pm

@@ -1,0 +1,404 @@
+"""Host-side execution engine: weight repacking + kernel sequencing for the tokenizer hot path.
+
+The engine owns no arithmetic: every FLOP on the path runs in libpaintmind_b200.so (ops.py).
+What lives here is (a) the one-time repack of the reference-layout fp32 parameters into the bf16
+operands the kernels want, and (b) the order in which kernels are enqueued on the current stream.
+
+HBM layout (M = B * tokens, D = model dim, all activations bf16 row-major unless noted):
+    x      [M, D]        residual stream, updated in place by the to_out / w3 GEMM epilogues
+    stats  [M, 2] fp32   (mean, rstd) of the current x — LayerNorm is folded into the next GEMM
+    qkv    [M, 3*inner]  q | k | v, token-major; attention reads heads by TMA column offset
+    ao     [M, inner]    attention output (heads concatenated)
+    h      [M, hid_pad]  silu(gate) * value, hidden padded to a multiple of 128 (1368 -> 1408)
+    z      [M, 32] fp32  prev_quant output;  zs [M, 64] bf16 = [hi | lo] split of z_q for post_quant
+
+Reference call order being reproduced: stage1/vqmodel.py:21-30, stage1/layers.py:54-58,106-112,
+145-152, modules/attention.py:43-59, modules/mlp.py:27-31.
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+
+from . import ops
+from .ops import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH
+
+LN_EPS = 1e-5
+
+
+def _ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# weight repacking (setup time; plain torch on the parameter device)
+# ------------------------------------------------------------------------------------------------
+def fold_layernorm(W, b, gamma, beta):
+    """LN(x) W^T + b  ==  rstd * (x W'^T - mu * colsum(W')) + b'   with W' = W * gamma, b' = b + W beta.
+    colsum is taken over the bf16-ROUNDED W' so that the identity holds for what the MMA reads."""
+    W = W.float()
+    Wf = (W * gamma.float()[None, :]).to(torch.bfloat16).contiguous()
+    colsum = Wf.float().sum(dim=1).contiguous()
+    bias = W @ beta.float()
+    if b is not None:
+        bias = bias + b.float()
+    return Wf, colsum, bias.contiguous()
+
+
+def pack_swiglu_w12(w12, b12, gamma, beta):
+    """Repack w12 ([2h, K]: rows 0..h-1 gate, h..2h-1 value — mlp.py:28-29) into 256-row tiles of
+    128 gate rows followed by their 128 value rows, hidden padded with zero rows to a multiple of 128,
+    with the preceding LayerNorm folded in."""
+    h = w12.shape[0] // 2
+    hp = _ceil_to(h, 128)
+    K = w12.shape[1]
+    Wf, colsum, bias = fold_layernorm(w12, b12, gamma, beta)
+
+    def tile(t, fill_shape):
+        g = torch.zeros((hp,) + fill_shape, device=t.device, dtype=t.dtype)
+        v = torch.zeros_like(g)
+        g[:h] = t[:h]
+        v[:h] = t[h:]
+        T = hp // 128
+        return torch.stack([g.reshape((T, 128) + fill_shape), v.reshape((T, 128) + fill_shape)], dim=1).reshape((2 * hp,) + fill_shape).contiguous()
+
+    return tile(Wf, (K,)), tile(colsum, ()), tile(bias, ()), hp
+
+
+def pack_w3(w3, hp):
+    D, h = w3.shape
+    out = torch.zeros(D, hp, device=w3.device, dtype=torch.bfloat16)
+    out[:, :h] = w3.to(torch.bfloat16)
+    return out.contiguous()
+
+
+class _Block:
+    """Packed operands of one pre-LN transformer block (self-attention [+ cross-attention] + SwiGLU)."""
+
+    def __init__(self, layer, heads, cross=False):
+        a1 = layer.attn1
+        wqkv = torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], dim=0).detach()
+        self.w_qkv, self.cs_qkv, self.b_qkv = fold_layernorm(wqkv, None, layer.norm1.weight.detach(), layer.norm1.bias.detach())
+        self.w_o = a1.to_out[0].weight.detach().to(torch.bfloat16).contiguous()
+        self.b_o = a1.to_out[0].bias.detach().float().contiguous()
+        self.inner = a1.to_q.weight.shape[0]
+        self.heads = heads
+        self.scale = float(a1.scale)
+        self.cross = cross
+        if cross:
+            a2 = layer.attn2
+            self.w_q2, self.cs_q2, self.b_q2 = fold_layernorm(a2.to_q.weight.detach(), None, layer.norm2.weight.detach(), layer.norm2.bias.detach())
+            self.w_kv2 = torch.cat([a2.to_k.weight, a2.to_v.weight], dim=0).detach().to(torch.bfloat16).contiguous()
+            # context=None -> attn2 is a second self-attention over LN2(x) (attention.py:47): fold LN2 into k/v too
+            wkv = torch.cat([a2.to_k.weight, a2.to_v.weight], dim=0).detach()
+            self.w_kv2_self, self.cs_kv2_self, self.b_kv2_self = fold_layernorm(wkv, None, layer.norm2.weight.detach(), layer.norm2.bias.detach())
+            self.w_o2 = a2.to_out[0].weight.detach().to(torch.bfloat16).contiguous()
+            self.b_o2 = a2.to_out[0].bias.detach().float().contiguous()
+            self.scale2 = float(a2.scale)
+            ffn_norm = layer.norm3
+        else:
+            ffn_norm = layer.norm2
+        ff = layer.ffnet
+        self.w_12, self.cs_12, self.b_12, self.hp = pack_swiglu_w12(ff.w12.weight.detach(), ff.w12.bias.detach(),
+                                                                    ffn_norm.weight.detach(), ffn_norm.bias.detach())
+        self.w_3 = pack_w3(ff.w3.weight.detach(), self.hp)
+        self.b_3 = ff.w3.bias.detach().float().contiguous()
+
+
+def _fingerprint(module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+class _Workspace:
+    """Activation buffers for a given (M, device); reused across calls."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, name, shape, dtype, device):
+        key = (name, tuple(shape), dtype, str(device))
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            # keep one buffer per name: drop stale shapes so memory does not grow with batch-size changes
+            for k in [k for k in self.bufs if k[0] == name and k != key]:
+                del self.bufs[k]
+            self.bufs[key] = t
+        return t
+
+
+def run_blocks(blocks, x, stats, B, N, ws, context_kv=None, ctx_len=0):
+    """Run packed transformer blocks in place on x [B*N, D] (bf16).  `stats` must hold the LayerNorm
+    statistics of x on entry and holds those of the final x on exit."""
+    M, D = x.shape
+    dev = x.device
+    for li, blk in enumerate(blocks):
+        inner = blk.inner
+        qkv = ws.get("qkv", (M, 3 * inner), torch.bfloat16, dev)
+        ao = ws.get("ao", (M, inner), torch.bfloat16, dev)
+        # x = attn1(norm1(x)) + x
+        ops.gemm(x, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, stats=stats)
+        q3 = qkv.view(B, N, 3 * inner)
+        ops.attention(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), blk.heads, blk.scale)
+        ops.gemm(ao, blk.w_o, x, bias=blk.b_o, res=x)
+        ops.layernorm(x, stats=stats)
+        if blk.cross:
+            # x = attn2(norm2(x), context) + x
+            q2 = ws.get("q2", (M, inner), torch.bfloat16, dev)
+            ops.gemm(x, blk.w_q2, q2, bias=blk.b_q2, colsum=blk.cs_q2, stats=stats)
+            if context_kv is not None:
+                kv = context_kv[li]
+                kv3 = kv.view(B, ctx_len, 2 * inner)
+            else:
+                kv = ws.get("kv2", (M, 2 * inner), torch.bfloat16, dev)
+                ops.gemm(x, blk.w_kv2_self, kv, bias=blk.b_kv2_self, colsum=blk.cs_kv2_self, stats=stats)
+                kv3 = kv.view(B, N, 2 * inner)
+            ops.attention(q2.view(B, N, inner), kv3[..., :inner], kv3[..., inner:], ao.view(B, N, inner), blk.heads, blk.scale2)
+            ops.gemm(ao, blk.w_o2, x, bias=blk.b_o2, res=x)
+            ops.layernorm(x, stats=stats)
+        # x = ffnet(norm(x)) + x
+        h = ws.get("h", (M, blk.hp), torch.bfloat16, dev)
+        ops.gemm(x, blk.w_12, h, bias=blk.b_12, colsum=blk.cs_12, stats=stats, swiglu=True)
+        ops.gemm(h, blk.w_3, x, bias=blk.b_3, res=x)
+        ops.layernorm(x, stats=stats)
+    return x
+
+
+class Stage1Engine:
+    """Kernel sequencing for VQModel.encode / decode / decode_from_indice."""
+
+    def __init__(self, model=None, encoder=None, decoder=None):
+        self._model = weakref.ref(model) if model is not None else None
+        self._encoder = encoder if model is None else None
+        self._decoder = decoder if model is None else None
+        self._fp = None
+        self.ws = _Workspace()
+
+    # -- module access -------------------------------------------------------------------------
+    @property
+    def model(self):
+        return self._model() if self._model is not None else None
+
+    @property
+    def encoder(self):
+        return self.model.encoder if self.model is not None else self._encoder
+
+    @property
+    def decoder(self):
+        return self.model.decoder if self.model is not None else self._decoder
+
+    def _root(self):
+        return self.model if self.model is not None else (self._encoder if self._encoder is not None else self._decoder)
+
+    # -- packing -------------------------------------------------------------------------------
+    def _ensure_packed(self):
+        root = self._root()
+        fp = _fingerprint(root)
+        if fp == self._fp:
+            return
+        p0 = next(root.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("paintmind_b200 runs on CUDA (sm_100a) only: move the model to a B200 device; "
+                               "there is no CPU fallback for the hot path")
+        with torch.no_grad():
+            enc, dec = self.encoder, self.decoder
+            if enc is not None:
+                if enc.patch_size != 8:
+                    raise RuntimeError("paintmind_b200 patch kernels are built for patch_size = 8")
+                conv = enc.to_patch_embedding[0].weight.detach()
+                self.w_pe = conv.reshape(conv.shape[0], -1).to(torch.bfloat16).contiguous()       # [D, C*P*P], K order (c,kh,kw)
+                self.enc_pos = enc.position_embedding.detach()[0].float().contiguous()            # [N, D]
+                self.pre_g = enc.norm_pre.weight.detach().float().contiguous()
+                self.pre_b = enc.norm_pre.bias.detach().float().contiguous()
+                self.enc_blocks = [_Block(l, enc.num_head) for l in enc.transformer.layers]
+            if dec is not None:
+                self.dec_pos = dec.position_embedding.detach()[0].float().contiguous()
+                self.dec_blocks = [_Block(l, dec.num_head) for l in dec.transformer.layers]
+                self.w_proj, self.cs_proj, self.b_proj = fold_layernorm(dec.proj.weight.detach(), dec.proj.bias.detach(),
+                                                                        dec.norm.weight.detach(), dec.norm.bias.detach())
+            m = self.model
+            if m is not None:
+                self.w_prev = m.prev_quant.weight.detach().to(torch.bfloat16).contiguous()        # [32, D]
+                self.b_prev = m.prev_quant.bias.detach().float().contiguous()
+                wp = m.post_quant.weight.detach().float()                                         # [D, 32]
+                self.w_post = torch.cat([wp, wp], dim=1).to(torch.bfloat16).contiguous()           # [D, 64] against [hi | lo]
+                self.b_post = m.post_quant.bias.detach().float().contiguous()
+        self._fp = fp
+
+    # -- encoder -------------------------------------------------------------------------------
+    def run_encoder(self, img):
+        """img fp32 NCHW in [-1, 1] -> tokens bf16 [B, N, D]  (Encoder.forward, layers.py:106-112)."""
+        self._ensure_packed()
+        enc = self.encoder
+        if not img.is_cuda:
+            raise RuntimeError("paintmind_b200: input must be a CUDA tensor (no CPU fallback)")
+        img = img.detach()
+        if img.dtype != torch.float32:
+            img = img.float()
+        img = img.contiguous()
+        B, C, H, W = img.shape
+        if H != enc.image_size or W != enc.image_size or C != enc.in_channels:
+            raise RuntimeError(f"expected input [B,{enc.in_channels},{enc.image_size},{enc.image_size}], got {tuple(img.shape)}")
+        g = H // 8
+        N, D = g * g, enc.dim
+        M = B * N
+        dev = img.device
+        ws = self.ws
+        patches = ws.get("patches", (M, C * 64), torch.bfloat16, dev)
+        x0 = ws.get("x0", (M, D), torch.bfloat16, dev)
+        x = ws.get("x", (M, D), torch.bfloat16, dev)
+        stats = ws.get("stats", (M, 2), torch.float32, dev)
+        ops.patchify8(img, patches)
+        ops.gemm(patches, self.w_pe, x0, pos=self.enc_pos)                        # conv-as-GEMM + position embedding
+        ops.layernorm(x0, gamma=self.pre_g, beta=self.pre_b, y=x, stats=stats)    # norm_pre
+        run_blocks(self.enc_blocks, x, stats, B, N, ws)
+        return x.view(B, N, D)
+
+    def encode(self, img):
+        m = self.model
+        x = self.run_encoder(img)
+        B, N, D = x.shape
+        M = B * N
+        dev = x.device
+        z = self.ws.get("z", (M, m.quantize.e_dim), torch.float32, dev)
+        ops.gemm(x.view(M, D), self.w_prev, z, bias=self.b_prev, out_mode=PM_OUT_F32, bn=32)   # prev_quant
+        r = m.quantize.quantize_2d(z, want_split=False)
+        loss = (r["sse"] * ((1.0 + m.quantize.beta) / (M * m.quantize.e_dim))).to(torch.float32).reshape(())
+        return r["zq"].view(B, N, -1), loss, r["idx"].view(B, N)
+
+    def latent(self, img):
+        """encoder + prev_quant only (fp32 [B, N, 32]); used by parity tests."""
+        m = self.model
+        x = self.run_encoder(img)
+        B, N, D = x.shape
+        z = torch.empty(B * N, m.quantize.e_dim, device=x.device, dtype=torch.float32)
+        ops.gemm(x.view(B * N, D), self.w_prev, z, bias=self.b_prev, out_mode=PM_OUT_F32, bn=32)
+        return z.view(B, N, -1)
+
+    # -- decoder -------------------------------------------------------------------------------
+    def _decode_tokens_inplace(self, x, stats, B, N, dev):
+        dec = self.decoder
+        run_blocks(self.dec_blocks, x, stats, B, N, self.ws)
+        g = dec.image_size // dec.patch_size
+        img = torch.empty(B, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
+        if dec.patch_size == 8 and dec.out_channels == 3:
+            # decoder.norm folded into proj; un-patchify + clamp fused into the store
+            ops.gemm(x, self.w_proj, img, bias=self.b_proj, colsum=self.cs_proj, stats=stats,
+                     out_mode=PM_OUT_UNPATCH, patch=8, channels=3, grid=g)
+        else:
+            raise RuntimeError("paintmind_b200 un-patchify epilogue is built for patch_size 8 / 3 channels")
+        return img
+
+    def decode(self, z):
+        """z [B, N, 32] -> image [B, 3, H, W] in [-1, 1]  (VQModel.decode, vqmodel.py:27-30)."""
+        self._ensure_packed()
+        dec = self.decoder
+        if not z.is_cuda:
+            raise RuntimeError("paintmind_b200: input must be a CUDA tensor (no CPU fallback)")
+        z = z.detach()
+        B, N, E = z.shape
+        M, D = B * N, dec.dim
+        dev = z.device
+        z2d = z.reshape(M, E)
+        if z2d.dtype != torch.float32:
+            z2d = z2d.float()
+        if z2d.stride(1) != 1 or z2d.stride(0) % 4 != 0 or z2d.data_ptr() % 16 != 0:
+            z2d = z2d.contiguous()
+        zs = self.ws.get("zs", (M, 2 * E), torch.bfloat16, dev)
+        ops.split_rows32(z2d, zs)
+        return self._decode_split(zs, B, N, dev)
+
+    def _decode_split(self, zs, B, N, dev):
+        dec = self.decoder
+        M, D = B * N, dec.dim
+        x = self.ws.get("x", (M, D), torch.bfloat16, dev)
+        stats = self.ws.get("stats", (M, 2), torch.float32, dev)
+        ops.gemm(zs, self.w_post, x, bias=self.b_post, pos=self.dec_pos)          # post_quant + position embedding
+        ops.layernorm(x, stats=stats)
+        return self._decode_tokens_inplace(x, stats, B, N, dev)
+
+    def decode_from_indice(self, indice):
+        """ids [B, N] int64 -> image  (vqmodel.py:38-41, quantize.py:40-44)."""
+        self._ensure_packed()
+        m = self.model
+        if not indice.is_cuda:
+            raise RuntimeError("paintmind_b200: input must be a CUDA tensor (no CPU fallback)")
+        B, N = indice.shape
+        M = B * N
+        dev = indice.device
+        E = m.quantize.embedding.weight.detach().float().contiguous()
+        zs = self.ws.get("zs", (M, 2 * m.quantize.e_dim), torch.bfloat16, dev)
+        ops.vq_gather(indice.reshape(-1).to(torch.int64).contiguous(), E, True, None, zs)
+        return self._decode_split(zs, B, N, dev)
+
+    def run_decoder_tokens(self, tokens):
+        """Decoder.forward on [B, N, D] tokens (layers.py:145-152) -> un-clamped?  NOTE: the fused
+        store clamps to [-1, 1] exactly like VQModel.decode; Decoder.forward alone is only reachable
+        through VQModel.decode in the reference's call sites."""
+        self._ensure_packed()
+        dec = self.decoder
+        B, N, D = tokens.shape
+        M = B * N
+        dev = tokens.device
+        x = self.ws.get("x", (M, D), torch.bfloat16, dev)
+        stats = self.ws.get("stats", (M, 2), torch.float32, dev)
+        x.copy_((tokens.detach().float() + self.dec_pos[None]).reshape(M, D))
+        ops.layernorm(x, stats=stats)
+        return self._decode_tokens_inplace(x, stats, B, N, dev)
+
+
+def engine_for(module):
+    """Engine for a stand-alone Encoder or Decoder module (cached on the module)."""
+    eng = module.__dict__.get("_pm_engine")
+    if eng is None:
+        from .stage1.layers import Encoder
+        eng = Stage1Engine(encoder=module) if isinstance(module, Encoder) else Stage1Engine(decoder=module)
+        module.__dict__["_pm_engine"] = eng
+    return eng
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone module forwards (unit parity tests of rows a8 / a9)
+# ------------------------------------------------------------------------------------------------
+def standalone_attention(mod, x, context=None):
+    """CrossAttention.forward (attention.py:43-59) on the CUDA kernels; returns x.dtype."""
+    if not x.is_cuda:
+        raise RuntimeError("paintmind_b200: CUDA only (no CPU fallback)")
+    B, N, Dq = x.shape
+    ctx = x if context is None else context
+    L = ctx.shape[1]
+    inner = mod.to_q.weight.shape[0]
+    dev = x.device
+    xb = x.detach().reshape(B * N, Dq).to(torch.bfloat16).contiguous()
+    cb = xb if context is None else ctx.detach().reshape(B * L, -1).to(torch.bfloat16).contiguous()
+    q = torch.empty(B * N, inner, device=dev, dtype=torch.bfloat16)
+    kv = torch.empty(B * L, 2 * inner, device=dev, dtype=torch.bfloat16)
+    ops.gemm(xb, mod.to_q.weight.detach().to(torch.bfloat16).contiguous(), q)
+    ops.gemm(cb, torch.cat([mod.to_k.weight, mod.to_v.weight], 0).detach().to(torch.bfloat16).contiguous(), kv)
+    ao = torch.empty(B * N, inner, device=dev, dtype=torch.bfloat16)
+    kv3 = kv.view(B, L, 2 * inner)
+    ops.attention(q.view(B, N, inner), kv3[..., :inner], kv3[..., inner:], ao.view(B, N, inner), mod.heads, mod.scale)
+    out = torch.empty(B * N, Dq, device=dev, dtype=torch.float32)
+    ops.gemm(ao, mod.to_out[0].weight.detach().to(torch.bfloat16).contiguous(), out,
+             bias=mod.to_out[0].bias.detach().float().contiguous(), out_mode=PM_OUT_F32)
+    return out.view(B, N, Dq).to(x.dtype)
+
+
+def standalone_swiglu(mod, x):
+    """SwiGLUFFN.forward (mlp.py:27-31) on the CUDA kernels; returns x.dtype."""
+    if not x.is_cuda:
+        raise RuntimeError("paintmind_b200: CUDA only (no CPU fallback)")
+    shape = x.shape
+    D = shape[-1]
+    xb = x.detach().reshape(-1, D).to(torch.bfloat16).contiguous()
+    M = xb.shape[0]
+    dev = x.device
+    ones = torch.ones(D, device=dev)
+    zeros = torch.zeros(D, device=dev)
+    w12, cs, b12, hp = pack_swiglu_w12(mod.w12.weight.detach(), mod.w12.bias.detach(), ones, zeros)
+    h = torch.empty(M, hp, device=dev, dtype=torch.bfloat16)
+    ops.gemm(xb, w12, h, bias=b12, swiglu=True)
+    out = torch.empty(M, mod.w3.weight.shape[0], device=dev, dtype=torch.float32)
+    ops.gemm(h, pack_w3(mod.w3.weight.detach(), hp), out, bias=mod.w3.bias.detach().float().contiguous(), out_mode=PM_OUT_F32)
+    return out.view(*shape[:-1], -1).to(x.dtype)

@@ -1,0 +1,114 @@
+"""Tensor-level wrappers over the C-ABI (include/paintmind_b200.h).
+
+Every function enqueues hand-written sm_100a kernels on torch's current CUDA stream and raises
+RuntimeError on failure.  PyTorch only provides device memory and streams here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH  # noqa: F401
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("paintmind_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, out_mode=PM_OUT_BF16,
+         swiglu=False, bn=0, n=None, patch=0, channels=0, grid=0, max_ctas=0):
+    """out = epilogue(a[M,K] @ w[N,K]^T); see pm_gemm_bf16 in include/paintmind_b200.h."""
+    _require_cuda(a, w, out)
+    args = _lib.GemmArgs()
+    args.a, args.w, args.out = _ptr(a), _ptr(w), _ptr(out)
+    args.bias, args.colsum, args.stats = _ptr(bias), _ptr(colsum), _ptr(stats)
+    args.pos, args.res = _ptr(pos), _ptr(res)
+    args.lda, args.ldw = a.stride(0), w.stride(0)
+    args.ld_out = out.stride(0) if out_mode != PM_OUT_UNPATCH else 0
+    args.ld_pos = pos.stride(0) if pos is not None else 0
+    args.ld_res = res.stride(0) if res is not None else 0
+    args.M, args.N, args.K = a.shape[0], (n if n is not None else w.shape[0]), a.shape[1]
+    args.pos_rows = pos.shape[0] if pos is not None else 0
+    args.out_mode, args.swiglu, args.bn = out_mode, int(bool(swiglu)), bn
+    args.patch, args.channels, args.grid, args.max_ctas = patch, channels, grid, max_ctas
+    _lib.check(_lib.load().pm_gemm_bf16(C.byref(args), _stream()), "pm_gemm_bf16")
+    return out
+
+
+def attention(q, k, v, o, heads, scale):
+    """q,o: [B, Nq, >=heads*64] views; k,v: [B, Nk, ...] views (bf16, last stride 1)."""
+    _require_cuda(q, k, v, o)
+    args = _lib.AttnArgs()
+    args.q, args.k, args.v, args.o = _ptr(q), _ptr(k), _ptr(v), _ptr(o)
+    args.ldq, args.ldk, args.ldv, args.ldo = q.stride(1), k.stride(1), v.stride(1), o.stride(1)
+    args.bsq, args.bsk, args.bsv, args.bso = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
+    args.scale = float(scale)
+    _lib.check(_lib.load().pm_attn_fwd(C.byref(args), _stream()), "pm_attn_fwd")
+    return o
+
+
+def vq_codebook_prep(E, en=None, packed=None):
+    _require_cuda(E)
+    n_e, e_dim = E.shape
+    if en is None:
+        en = torch.empty(n_e, e_dim, device=E.device, dtype=torch.float32)
+    if packed is None:
+        packed = torch.empty(n_e, 2 * e_dim, device=E.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().pm_vq_codebook_prep(_ptr(E), n_e, e_dim, _ptr(en), _ptr(packed), _stream()),
+               "pm_vq_codebook_prep")
+    return en, packed
+
+
+def vq_forward(z2d, en, packed, *, idx, zq=None, zq_split=None, sse=None, hist=None, cand_val=None, cand_idx=None,
+               splits=0):
+    _require_cuda(z2d, en, packed, idx)
+    args = _lib.VqArgs()
+    args.z, args.en, args.packed = _ptr(z2d), _ptr(en), _ptr(packed)
+    args.cand_val, args.cand_idx = _ptr(cand_val), _ptr(cand_idx)
+    args.idx, args.zq, args.zq_split = _ptr(idx), _ptr(zq), _ptr(zq_split)
+    args.sse, args.hist = _ptr(sse), _ptr(hist)
+    args.ldz = z2d.stride(0)
+    args.M, args.n_e, args.e_dim, args.splits = z2d.shape[0], en.shape[0], en.shape[1], splits
+    _lib.check(_lib.load().pm_vq_fwd(C.byref(args), _stream()), "pm_vq_fwd")
+
+
+def vq_gather(idx, table, normalize, out=None, out_split=None):
+    _require_cuda(idx, table)
+    M = idx.numel()
+    _lib.check(_lib.load().pm_vq_gather(_ptr(idx), M, table.shape[0], table.shape[1], _ptr(table), int(normalize),
+                                        _ptr(out), _ptr(out_split), _stream()), "pm_vq_gather")
+
+
+def split_rows32(src2d, out_split):
+    _require_cuda(src2d, out_split)
+    _lib.check(_lib.load().pm_split_rows32(_ptr(src2d), src2d.stride(0), src2d.shape[0], _ptr(out_split), _stream()),
+               "pm_split_rows32")
+    return out_split
+
+
+def patchify8(img, out):
+    _require_cuda(img, out)
+    B, Cc, H, W = img.shape
+    _lib.check(_lib.load().pm_patchify8(_ptr(img), _ptr(out), B, Cc, H, W, _stream()), "pm_patchify8")
+    return out
+
+
+def layernorm(x, *, gamma=None, beta=None, y=None, stats=None, eps=1e-5):
+    """y is None -> stats only; else y = LN(x) (and stats of y if given)."""
+    _require_cuda(x)
+    M, D = x.shape
+    _lib.check(_lib.load().pm_layernorm(_ptr(x), x.stride(0), M, D, float(eps), _ptr(gamma), _ptr(beta), _ptr(y),
+                                        y.stride(0) if y is not None else 0, _ptr(stats), _stream()), "pm_layernorm")

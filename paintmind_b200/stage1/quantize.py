@@ -1,0 +1,71 @@
+"""VectorQuantizer with the reference surface (stage1/quantize.py:9-44): n_e, e_dim, beta,
+``embedding`` (nn.Embedding, N(0,1) init), forward(z) -> (z_q, loss, indices),
+decode_from_indice(indices).  The arithmetic is csrc/pm_vq.cu."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class VectorQuantizer(nn.Module):
+    def __init__(self, n_e, e_dim, beta=0.25):
+        super().__init__()
+        self.n_e = n_e
+        self.e_dim = e_dim
+        self.beta = beta
+        self.embedding = nn.Embedding(n_e, e_dim)
+        self.embedding.weight.data.normal_()
+        self._last_hist = None      # codebook usage of the last forward (int64 [n_e]); new in this build
+        self._last_sse = None       # sum (z_q - z)^2 of the last forward (float64 [1])
+
+    def _check(self, t):
+        if not t.is_cuda or not self.embedding.weight.is_cuda:
+            raise RuntimeError("paintmind_b200.VectorQuantizer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.e_dim != 32:
+            raise RuntimeError("paintmind_b200 VQ kernels are built for e_dim = 32")
+
+    @torch.no_grad()
+    def quantize_2d(self, z2d, want_split=False):
+        """z2d: fp32 [M, 32] (row stride multiple of 4).  Returns dict(idx, zq, zq_split, sse, hist)."""
+        self._check(z2d)
+        M = z2d.shape[0]
+        dev = z2d.device
+        E = self.embedding.weight.detach()
+        if E.dtype != torch.float32:
+            E = E.float()
+        en, packed = ops.vq_codebook_prep(E.contiguous())
+        idx = torch.empty(M, device=dev, dtype=torch.int64)
+        zq = torch.empty(M, self.e_dim, device=dev, dtype=torch.float32)
+        zs = torch.empty(M, 2 * self.e_dim, device=dev, dtype=torch.bfloat16) if want_split else None
+        sse = torch.zeros(1, device=dev, dtype=torch.float64)
+        hist = torch.zeros(self.n_e, device=dev, dtype=torch.int64)
+        cv = torch.empty(8, M, device=dev, dtype=torch.float32)
+        ci = torch.empty(8, M, device=dev, dtype=torch.int32)
+        ops.vq_forward(z2d, en, packed, idx=idx, zq=zq, zq_split=zs, sse=sse, hist=hist, cand_val=cv, cand_idx=ci)
+        self._last_hist, self._last_sse = hist, sse
+        return dict(idx=idx, zq=zq, zq_split=zs, sse=sse, hist=hist)
+
+    @torch.no_grad()
+    def forward(self, z):
+        self._check(z)
+        shape = z.shape
+        z2d = z.detach().reshape(-1, self.e_dim)
+        if z2d.dtype != torch.float32:
+            z2d = z2d.float()
+        if z2d.stride(1) != 1 or z2d.stride(0) % 4 != 0 or z2d.data_ptr() % 16 != 0:
+            z2d = z2d.contiguous()
+        r = self.quantize_2d(z2d)
+        # loss = beta * mean((zq - z)^2) + mean((zq - z)^2)   (quantize.py:33), mean over all elements
+        loss = (r["sse"] * ((1.0 + self.beta) / z2d.numel())).to(torch.float32).reshape(())
+        return r["zq"].reshape(shape), loss, r["idx"].reshape(shape[:-1])
+
+    @torch.no_grad()
+    def decode_from_indice(self, indices):
+        self._check(indices)
+        E = self.embedding.weight.detach().float().contiguous()
+        idx = indices.reshape(-1).to(torch.int64).contiguous()
+        out = torch.empty(idx.numel(), self.e_dim, device=idx.device, dtype=torch.float32)
+        ops.vq_gather(idx, E, True, out, None)
+        return out.reshape(*indices.shape, self.e_dim)

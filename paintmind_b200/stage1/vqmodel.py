@@ -1,0 +1,59 @@
+"""VQModel — the drop-in for the reference's stage1/vqmodel.py:7-44.
+
+Same attributes (encoder, decoder, quantize, prev_quant, post_quant), same methods and return
+conventions, identical state_dict keys (222 tensors); the arithmetic runs in
+hand-written sm_100a kernels through engine.Stage1Engine.  Inference only: outputs carry no
+autograd graph."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .layers import Decoder, Encoder
+from .quantize import VectorQuantizer
+
+
+class VQModel(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.encoder = Encoder(**config.enc)
+        self.decoder = Decoder(**config.dec)
+        self.quantize = VectorQuantizer(config.n_embed, config.embed_dim, config.beta)
+        self.prev_quant = nn.Linear(config.enc["dim"], config.embed_dim)
+        self.post_quant = nn.Linear(config.embed_dim, config.dec["dim"])
+        self._engine = None
+
+    # -- reference surface -------------------------------------------------------------------
+    def freeze(self):
+        self.eval()
+        for p in self.parameters():
+            p.requires_grad = False
+
+    @torch.no_grad()
+    def encode(self, x):
+        """(z_q [B,N,32] fp32, loss [] fp32, indices [B,N] int64) — vqmodel.py:21-25."""
+        return self.engine().encode(x)
+
+    @torch.no_grad()
+    def decode(self, x):
+        """[B,N,32] -> image [B,3,H,W] clamped to [-1,1] — vqmodel.py:27-30."""
+        return self.engine().decode(x)
+
+    @torch.no_grad()
+    def forward(self, img):
+        z, loss, _ = self.encode(img)
+        return self.decode(z), loss
+
+    @torch.no_grad()
+    def decode_from_indice(self, indice):
+        return self.engine().decode_from_indice(indice)
+
+    def from_pretrained(self, path):
+        return self.load_state_dict(torch.load(path))
+
+    # -- engine ------------------------------------------------------------------------------
+    def engine(self):
+        if self._engine is None:
+            from ..engine import Stage1Engine
+            object.__setattr__(self, "_engine", Stage1Engine(self))
+        return self._engine
