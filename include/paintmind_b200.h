@@ -140,9 +140,37 @@ int pm_split_rows32(const float* src, int64_t ld, int32_t M, void* out_split, vo
  *                  y == NULL: only stats[row] = (mean, rstd) (feeds the LN-folded GEMM epilogue);
  *                  y != NULL: y = LN(x) * gamma + beta (bf16) and, if stats != NULL, the stats of y.
  * ------------------------------------------------------------------------------------------- */
+/* pm_cast_f32_bf16 : fp32 -> bf16 (n % 8 == 0); the text context entering cross-attention k/v (transformer.py:84-86). */
+int pm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int pm_patchify8(const float* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 int pm_layernorm(const void* x, int64_t ldx, int32_t M, int32_t D, float eps, const float* gamma,
                  const float* beta, void* y, int64_t ldy, float* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaskGIT step tail (generate.py:159-181), one pass over the fp32 logits [M = B*N, V]:
+ *   pm_maskgit_sample : top_k filter (generate.py:33-37) + gumbel_sample (:40-46) + mask fill (:166-168)
+ *                       + confidence score 1 - softmax(logits)[pred], -1e5 at unmasked positions (:170-173).
+ *                       noise != NULL injects the uniforms the reference would have drawn at [row, index]
+ *                       (parity tests); otherwise Philox4x32-10 keyed on (seed, row, index, offset).
+ *                       topk in [1, 32].
+ *   pm_maskgit_remask : ids.scatter(1, scores.topk(k).indices, mask_id) per image (generate.py:175-179);
+ *                       ties at the k-th score resolve to the lower token index.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pm_maskgit_sample_args {
+  const float* logits;
+  const float* noise;     /* optional [M, V] uniforms in [0,1) */
+  int64_t* ids;           /* [M] in/out, optional */
+  int64_t* pred_ids;      /* [M] out */
+  float* scores;          /* [M] out */
+  int64_t ld, ld_noise;
+  int64_t mask_id;
+  uint64_t seed, offset;
+  int32_t M, V, topk;
+  float temperature;
+} pm_maskgit_sample_args;
+
+int pm_maskgit_sample(const pm_maskgit_sample_args* args, void* stream);
+int pm_maskgit_remask(const float* scores, int64_t* ids, int32_t B, int32_t N, int32_t k, int64_t mask_id, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,16 @@ class VqArgs(C.Structure):
     ]
 
 
+class MaskgitSampleArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("noise", C.c_void_p), ("ids", C.c_void_p), ("pred_ids", C.c_void_p),
+        ("scores", C.c_void_p),
+        ("ld", C.c_int64), ("ld_noise", C.c_int64), ("mask_id", C.c_int64),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("M", C.c_int32), ("V", C.c_int32), ("topk", C.c_int32), ("temperature", C.c_float),
+    ]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -87,6 +97,9 @@ EXPORTS = {
     "pm_split_rows32": [_p, _i64, _i32, _p, _p],
     "pm_patchify8": [_p, _p, _i32, _i32, _i32, _i32, _p],
     "pm_layernorm": [_p, _i64, _i32, _i32, _f, _p, _p, _p, _i64, _p, _p],
+    "pm_cast_f32_bf16": [_p, _p, _i64, _p],
+    "pm_maskgit_sample": [C.POINTER(MaskgitSampleArgs), _p],
+    "pm_maskgit_remask": [_p, _p, _i32, _i32, _i32, _i64, _p],
 }
 
 

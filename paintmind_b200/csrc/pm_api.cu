@@ -108,4 +108,23 @@ int pm_layernorm(const void* x, int64_t ldx, int32_t M, int32_t D, float eps, co
   return pm_layernorm_launch(x, ldx, M, D, eps, gamma, beta, y, ldy, stats, static_cast<cudaStream_t>(stream));
 }
 
+int pm_maskgit_sample(const pm_maskgit_sample_args* a, void* stream) {
+  if (a == nullptr) return PM_ERR_INVALID;
+  MaskgitParams p;
+  p.logits = a->logits; p.ld = a->ld; p.M = a->M; p.V = a->V; p.topk = a->topk; p.temperature = a->temperature;
+  p.noise = a->noise; p.ld_noise = a->ld_noise; p.seed = a->seed; p.offset = a->offset;
+  p.ids = reinterpret_cast<long long*>(a->ids);
+  p.pred_ids = reinterpret_cast<long long*>(a->pred_ids);
+  p.scores = a->scores; p.mask_id = a->mask_id;
+  return pm_maskgit_sample_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int pm_maskgit_remask(const float* scores, int64_t* ids, int32_t B, int32_t N, int32_t k, int64_t mask_id, void* stream) {
+  return pm_maskgit_remask_launch(scores, reinterpret_cast<long long*>(ids), B, N, k, mask_id, static_cast<cudaStream_t>(stream));
+}
+
+int pm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  return pm_cast_launch(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -55,7 +55,13 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int n_tiles, int bn) {
   return t;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// silu(x) = x * sigmoid(x) with two MUFU ops (ex2.approx, rcp.approx; ~1e-6 relative error)
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 template <int BN, int OUT_MODE, bool SWIGLU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -205,6 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mu = st.x;
         rstd = st.y;
       }
+      const float nrmu = -rstd * mu;     // LN fold: rstd * (acc - mu * colsum) + bias == acc * rstd + (nrmu * colsum + bias)
       const float* pos_row = nullptr;
       if (p.pos != nullptr && row_ok) pos_row = p.pos + static_cast<size_t>(row % p.pos_rows) * p.ld_pos;
       named_bar_sync(1, 128);
@@ -236,8 +243,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float bvs[4] = {bv.x, bv.y, bv.z, bv.w}, cvs[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float a = rstd * (__uint_as_float(rg[j + t]) - mu * cgs[t]) + bgs[t];
-                const float b = rstd * (__uint_as_float(rv[j + t]) - mu * cvs[t]) + bvs[t];
+                const float a = fmaf(__uint_as_float(rg[j + t]), rstd, fmaf(nrmu, cgs[t], bgs[t]));
+                const float b = fmaf(__uint_as_float(rv[j + t]), rstd, fmaf(nrmu, cvs[t], bvs[t]));
                 v[h * 32 + j + t] = silu_f(a) * b;
               }
             }
@@ -252,7 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float bbs[4] = {bb.x, bb.y, bb.z, bb.w}, ccs[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t)
-                v[h * 32 + j + t] = rstd * (__uint_as_float(ra[j + t]) - mu * ccs[t]) + bbs[t];
+                v[h * 32 + j + t] = fmaf(__uint_as_float(ra[j + t]), rstd, fmaf(nrmu, ccs[t], bbs[t]));
             }
             if (pos_row != nullptr) {
               const int col0 = tc.n0 + oc;

@@ -51,7 +51,24 @@ struct VqParams {
   unsigned long long* hist;        // [n_e] += usage counts, optional
 };
 
+struct MaskgitParams {
+  const float* logits;             // [M, V] fp32, row pitch ld
+  int64_t ld;
+  int M, V, topk;
+  float temperature;
+  const float* noise;              // optional injected uniforms [M, V] (row pitch ld_noise)
+  int64_t ld_noise;
+  unsigned long long seed, offset; // Philox key / stream offset when noise == nullptr
+  long long* ids;                  // [M] in/out (masked positions filled with the prediction), optional
+  long long* pred_ids;             // [M] out
+  float* scores;                   // [M] out: 1 - p(pred) at masked positions, -1e5 elsewhere
+  long long mask_id;
+};
+
 int pm_num_sms();
+int pm_cast_launch(const float* src, void* dst, long long n, cudaStream_t stream);
+int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream);
+int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, cudaStream_t stream);
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
 int pm_vq_codebook_prep_launch(const float* E, int n_e, float* en, void* packed, cudaStream_t stream);
 int pm_vq_launch(const VqParams& p, cudaStream_t stream);

@@ -1,0 +1,193 @@
+// pm_maskgit.cu — the HBM-bound tail of a MaskGIT step (sm_100a), one pass over the logits.
+//
+// Replaces, for one call of Pipeline.sample (reference generate.py:159-181):
+//   top_k (generate.py:33-37)            keep the k largest logits per token, -inf elsewhere
+//   gumbel_sample (generate.py:40-46)    argmax(filtered / max(T, 1e-10) - log(-log(u)))
+//   fill + confidence (generate.py:166-173)  ids = where(ids == mask, pred, ids);
+//                                        score = 1 - softmax(logits)[pred]; unmasked -> -1e5
+//   re-mask (generate.py:175-179)        ids.scatter(topk(scores, k).indices, mask_id)
+// The reference reads the [B, N, 8192] fp32 logits >= 4 times and draws a same-sized uniform tensor;
+// here one warp streams each 32 KB row once (online max / sum-exp + per-lane top-k lists merged with
+// warp shuffles) and draws only the k uniforms it needs (Philox4x32-10 keyed on (seed, row, index)),
+// or reads them from an injected noise tensor for parity tests.
+#include "pm_common.cuh"
+#include "pm_kernels.h"
+
+namespace pm {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (index, row, offset, 0), key = seed
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t row, uint32_t index, uint32_t offset) {
+  uint32_t c0 = index, c1 = row, c2 = offset, c3 = 0x9e3779b9u;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return static_cast<float>(c0 >> 8) * (1.0f / 16777216.0f);   // [0, 1) with 24 random bits, like torch's uniform_
+}
+
+template <int KMAX>
+struct TopList {
+  float v[KMAX];
+  int i[KMAX];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) { v[t] = -INFINITY; i[t] = 0x7fffffff; }
+  }
+  // insert (x, xi) into the descending list; ties keep the lower index first
+  __device__ __forceinline__ void insert(float x, int xi) {
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) {
+      const bool gt = (x > v[t]) || (x == v[t] && xi < i[t]);
+      const float tv = v[t]; const int ti = i[t];
+      v[t] = gt ? x : tv;  i[t] = gt ? xi : ti;
+      x = gt ? tv : x;     xi = gt ? ti : xi;
+    }
+  }
+  __device__ __forceinline__ void pop() {
+#pragma unroll
+    for (int t = 0; t + 1 < KMAX; ++t) { v[t] = v[t + 1]; i[t] = i[t + 1]; }
+    v[KMAX - 1] = -INFINITY; i[KMAX - 1] = 0x7fffffff;
+  }
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+maskgit_sample_kernel(const MaskgitParams p) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  const float* x = p.logits + static_cast<size_t>(row) * p.ld;
+  const int k = p.topk;
+
+  TopList<KMAX> top;
+  top.init();
+  float m = -INFINITY, s = 0.0f;      // lane-local online softmax state
+  const int nvec = p.V >> 2;
+  for (int c0 = lane; c0 < nvec; c0 += 32 * 4) {
+    // 4 independent 16-byte loads in flight per lane
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32;
+      q[u] = (c < nvec) ? __ldcs(reinterpret_cast<const float4*>(x) + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float cm = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cm = fmaxf(cm, fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w)));
+    if (cm > m) { s *= __expf(m - cm); m = cm; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int base = (c0 + u * 32) * 4;
+      const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        s += __expf(e[t] - m);
+        if (e[t] > top.v[KMAX - 1] && k > 0) top.insert(e[t], base + t);   // rare after the first few chunks
+      }
+    }
+  }
+  // warp-wide softmax statistics
+  float mw = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+  float sw = (m == -INFINITY) ? 0.0f : s * __expf(m - mw);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
+
+  // merge the per-lane lists: k rounds of warp arg-max (ties -> lower index); lane r keeps winner r
+  float my_v = -INFINITY;
+  int my_i = 0x7fffffff;
+  for (int r = 0; r < k; ++r) {
+    float bv = top.v[0];
+    int bi = top.i[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (top.i[0] == bi && top.v[0] == bv) top.pop();
+    if (lane == r) { my_v = bv; my_i = bi; }
+  }
+
+  // gumbel-perturbed arg-max over the k survivors (generate.py:45-46)
+  float score = -INFINITY;
+  if (lane < k && my_i != 0x7fffffff) {
+    float u;
+    if (p.noise != nullptr) u = p.noise[static_cast<size_t>(row) * p.ld_noise + my_i];
+    else u = philox_uniform(p.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(my_i), static_cast<uint32_t>(p.offset));
+    const float inner = -logf(fmaxf(u, 1e-20f));
+    const float g = -logf(fmaxf(inner, 1e-20f));
+    score = my_v / fmaxf(p.temperature, 1e-10f) + g;
+  }
+  float bs = score;
+  int bi = (lane < k) ? my_i : 0x7fffffff;
+  float bl = my_v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; bl = ol; }
+  }
+  if (lane == 0) {
+    const long long pred = static_cast<long long>(bi);
+    const float prob = __expf(bl - mw) / sw;                 // softmax(logits)[pred], unfiltered, T = 1
+    if (p.pred_ids != nullptr) p.pred_ids[row] = pred;
+    bool is_mask = true;
+    if (p.ids != nullptr) {
+      is_mask = (p.ids[row] == p.mask_id);
+      if (is_mask) p.ids[row] = pred;                        // fill the mask, keep the unmasked
+    }
+    if (p.scores != nullptr) p.scores[row] = is_mask ? (1.0f - prob) : -1e5f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// re-mask: per image, the k highest scores get mask_id (ties: lower token index first).
+// rank_i = #{j : s_j > s_i  or (s_j == s_i and j < i)};  token i is re-masked iff rank_i < k.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+maskgit_remask_kernel(const float* __restrict__ scores, long long* __restrict__ ids, int N, int k, long long mask_id) {
+  extern __shared__ float sm_scores[];
+  const int b = blockIdx.x;
+  const float* s = scores + static_cast<size_t>(b) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sm_scores[i] = s[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float si = sm_scores[i];
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < N; ++j) {
+      const float sj = sm_scores[j];                  // broadcast read
+      rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+    }
+    if (rank < k) ids[static_cast<size_t>(b) * N + i] = mask_id;
+  }
+}
+
+int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
+  if (p.logits == nullptr || p.M <= 0 || p.V <= 0 || (p.V & 3) != 0 || (p.ld & 3) != 0) return PM_ERR_INVALID;
+  if (p.topk < 1 || p.topk > 32 || p.topk > p.V) return PM_ERR_INVALID;
+  const int threads = 256;
+  const int blocks = (p.M + 7) / 8;
+  if (p.topk <= 8) maskgit_sample_kernel<8><<<blocks, threads, 0, stream>>>(p);
+  else maskgit_sample_kernel<32><<<blocks, threads, 0, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, cudaStream_t stream) {
+  if (scores == nullptr || ids == nullptr || B <= 0 || N <= 0 || k < 0 || N > 12288) return PM_ERR_INVALID;
+  const int threads = N < 1024 ? ((N + 31) / 32) * 32 : 1024;
+  maskgit_remask_kernel<<<B, threads, N * sizeof(float), stream>>>(scores, ids, N, k, mask_id);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pm

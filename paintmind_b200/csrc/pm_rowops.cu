@@ -137,6 +137,22 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int D,
   }
 }
 
+// fp32 -> bf16 (round to nearest even), n % 8 == 0, 16-byte aligned; used for the text context
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
+  const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+  reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+
+int pm_cast_launch(const float* src, void* dst, long long n, cudaStream_t stream) {
+  if (src == nullptr || dst == nullptr || n <= 0 || (n & 7) != 0) return PM_ERR_INVALID;
+  const long long n8 = n >> 3;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n8);
+  return static_cast<int>(cudaGetLastError());
+}
+
 int pm_patchify_launch(const float* img, void* out, int B, int C, int H, int W, int P, cudaStream_t stream) {
   if (img == nullptr || out == nullptr || P != 8 || (H % 8) != 0 || (W % 8) != 0 || B <= 0 || C <= 0) return PM_ERR_INVALID;
   const long long total = static_cast<long long>(B) * C * H * (W / 8);

@@ -348,6 +348,108 @@ class Stage1Engine:
         return self._decode_tokens_inplace(x, stats, B, N, dev)
 
 
+class Stage2Engine:
+    """Kernel sequencing for CondTransformer.forward (stage2/transformer.py:80-93)."""
+
+    def __init__(self, transformer):
+        self._tr = weakref.ref(transformer)
+        self._fp = None
+        self.ws = _Workspace()
+        self._ctx_key = None
+        self._ctx_kv = None
+
+    @property
+    def tr(self):
+        return self._tr()
+
+    def _ensure_packed(self):
+        tr = self.tr
+        fp = _fingerprint(tr)
+        if fp == self._fp:
+            return
+        p0 = next(tr.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("paintmind_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if tr.in_dim != 32:
+            raise RuntimeError("paintmind_b200 stage-2 token path is built for 32-d tokens")
+        with torch.no_grad():
+            wt = tr.token_proj.weight.detach().float()
+            self.w_tok = torch.cat([wt, wt], dim=1).to(torch.bfloat16).contiguous()          # against [hi | lo]
+            self.b_tok = tr.token_proj.bias.detach().float().contiguous()
+            self.pos = tr.position_embedding.detach()[0].float().contiguous()
+            self.w_ctx = None
+            if isinstance(tr.context_proj, torch.nn.Linear):
+                self.w_ctx = tr.context_proj.weight.detach().to(torch.bfloat16).contiguous()
+            self.blocks = [_Block(l, tr.num_head, cross=True) for l in tr.layers]
+            self.w_logits, self.cs_logits, self.b_logits = fold_layernorm(tr.to_logits.weight.detach(), tr.to_logits.bias.detach(),
+                                                                          tr.norm.weight.detach(), tr.norm.bias.detach())
+        self._fp = fp
+        self._ctx_key = None
+
+    def _context_kv(self, context):
+        """Per-layer K/V projections of the (fixed) text context; cached across MaskGIT steps."""
+        key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
+        if key == self._ctx_key:
+            return self._ctx_kv
+        B, L, Dc = context.shape
+        dev = context.device
+        c2d = context.detach().reshape(B * L, Dc)
+        cb = torch.empty(B * L, Dc, device=dev, dtype=torch.bfloat16)
+        ops.cast_bf16(c2d.float().contiguous() if c2d.dtype != torch.float32 or not c2d.is_contiguous() else c2d, cb)
+        if self.w_ctx is not None:
+            cp = torch.empty(B * L, self.w_ctx.shape[0], device=dev, dtype=torch.bfloat16)
+            ops.gemm(cb, self.w_ctx, cp)
+            cb = cp
+        kvs = []
+        for blk in self.blocks:
+            kv = torch.empty(B * L, 2 * blk.inner, device=dev, dtype=torch.bfloat16)
+            ops.gemm(cb, blk.w_kv2, kv)
+            kvs.append(kv)
+        self._ctx_key, self._ctx_kv = key, kvs
+        return kvs
+
+    def _run(self, zs, B, N, context):
+        tr = self.tr
+        dev = zs.device
+        M, D = B * N, tr.dim
+        if N != self.pos.shape[0]:
+            raise RuntimeError(f"expected {self.pos.shape[0]} tokens per sample, got {N}")
+        x = self.ws.get("x", (M, D), torch.bfloat16, dev)
+        stats = self.ws.get("stats", (M, 2), torch.float32, dev)
+        ops.gemm(zs, self.w_tok, x, bias=self.b_tok, pos=self.pos)               # token_proj + position embedding
+        ops.layernorm(x, stats=stats)
+        kvs, L = None, 0
+        if context is not None:
+            kvs = self._context_kv(context)
+            L = context.shape[1]
+        run_blocks(self.blocks, x, stats, B, N, self.ws, context_kv=kvs, ctx_len=L)
+        logits = torch.empty(M, tr.num_classes, device=dev, dtype=torch.float32)
+        ops.gemm(x, self.w_logits, logits, bias=self.b_logits, colsum=self.cs_logits, stats=stats, out_mode=PM_OUT_F32)
+        return logits.view(B, N, tr.num_classes)
+
+    def forward(self, tokens, context=None):
+        self._ensure_packed()
+        if not tokens.is_cuda:
+            raise RuntimeError("paintmind_b200: input must be a CUDA tensor (no CPU fallback)")
+        B, N, E = tokens.shape
+        t2d = tokens.detach().reshape(B * N, E)
+        if t2d.dtype != torch.float32:
+            t2d = t2d.float()
+        if t2d.stride(1) != 1 or t2d.stride(0) % 4 != 0 or t2d.data_ptr() % 16 != 0:
+            t2d = t2d.contiguous()
+        zs = self.ws.get("zs", (B * N, 2 * E), torch.bfloat16, tokens.device)
+        ops.split_rows32(t2d, zs)
+        return self._run(zs, B, N, context)
+
+    def forward_from_ids(self, ids, table, context=None):
+        """ids2tokens (generate.py:148-157) fused with the token split: ids -> [hi | lo] rows of the raw table."""
+        self._ensure_packed()
+        B, N = ids.shape
+        zs = self.ws.get("zs", (B * N, 2 * table.shape[1]), torch.bfloat16, ids.device)
+        ops.vq_gather(ids.reshape(-1), table, False, None, zs)
+        return self._run(zs, B, N, context)
+
+
 def engine_for(module):
     """Engine for a stand-alone Encoder or Decoder module (cached on the module)."""
     eng = module.__dict__.get("_pm_engine")

@@ -1,0 +1,163 @@
+"""Pipeline — the MaskGIT sampling half of the reference's generate.py (:25-46, :49-76, :125-134,
+:148-198) on the CUDA kernels.  Same constructor, attributes (vqgan, text_model, transformer,
+mask_token, mask_token_id, image_size, patch_size, num_tokens) and method signatures.
+
+Out of scope here: the T5 text encoder (frozen third-party model, needs network
+weights — `text_model` is a pluggable callable, by default seeded random embeddings as in BASELINE
+config 5), the training forward (random_masking / loss / forward) and inpaint / outpaint (broken as
+shipped in the reference).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .config import ver2cfg
+
+
+def mask_schedule(ratio):
+    """cos(pi/2 * ratio) in numpy float64 (generate.py:25-26)."""
+    return np.cos(math.pi / 2.0 * ratio)
+
+
+class RandomTextEmbedder(nn.Module):
+    """Stand-in for the frozen T5 embedder (modules/encoder.py:18-42, out of scope): seeded random
+    [B, 77, dim] embeddings, the input BASELINE config 5 prescribes.  Replace `Pipeline.text_model`
+    with any callable list[str] -> [B, L, context_dim] tensor to plug a real encoder in."""
+
+    def __init__(self, dim=1024, length=77, seed=1234):
+        super().__init__()
+        self.dim, self.length, self.seed = dim, length, seed
+
+    def forward(self, text):
+        g = torch.Generator().manual_seed(self.seed)
+        return torch.randn(len(text), self.length, self.dim, generator=g)
+
+
+class Pipeline(nn.Module):
+    def __init__(self, config, stage1_pretrained=True, stage1_checkpoint_path=None):
+        super().__init__()
+        from .factory import create_model
+        from .stage2 import CondTransformer
+        t5_txt_dim = {"t5-l": 1024, "t5-xl": 2048}
+        self.vqgan = create_model(arch="vqgan", version=config.stage1, pretrained=stage1_pretrained,
+                                  checkpoint_path=stage1_checkpoint_path)
+        self.vqgan.freeze()
+        self.text_model = RandomTextEmbedder(t5_txt_dim[config.t5])
+        vq_cfg = ver2cfg[config.stage1]
+        self.image_size = vq_cfg["enc"]["image_size"]
+        self.patch_size = vq_cfg["enc"]["patch_size"]
+        self.num_tokens = (self.image_size // self.patch_size) ** 2
+        self.transformer = CondTransformer(
+            vq_cfg["embed_dim"], config.dim, self.num_tokens, config.dim_head, config.mlp_dim,
+            config.num_head, config.depth, config.dropout, t5_txt_dim[config.t5], vq_cfg["n_embed"])
+        self.mask_token = nn.Parameter(torch.zeros(1, vq_cfg["embed_dim"]))
+        self.mask_token_id = vq_cfg["n_embed"]
+        nn.init.normal_(self.mask_token, std=0.02)
+        self._rng_seed = None
+        self._rng_calls = 0
+        self._table = None
+        self._table_fp = None
+
+    def from_pretrained(self, path):
+        return self.load_state_dict(torch.load(path))
+
+    # ---- training-time members of the reference: out of scope --------------------------------
+    def random_masking(self, x, mask_ratio):
+        raise NotImplementedError("training-time masking (generate.py:78-108) is out of scope of the inference hot path")
+
+    def loss(self, logit, label, masks):
+        raise NotImplementedError("training loss (generate.py:110-123) is out of scope of the inference hot path")
+
+    def forward(self, img, text=None, mask_ratio=0.75):
+        raise NotImplementedError("the stage-2 training forward (generate.py:136-146) is out of scope; use generate()/sample()")
+
+    def inpaint(self, *a, **k):
+        raise NotImplementedError("inpaint is broken as shipped in the reference (float ids, generate.py:206-210) and out of scope")
+
+    outpaint = inpaint
+
+    # ---- hot path ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def to_latent(self, img, text=None):
+        x, _, indices = self.vqgan.encode(img)
+        if text is not None:
+            text = self._embed_text(text, img.device)
+        return x, indices, text
+
+    def _embed_text(self, text, device):
+        if torch.is_tensor(text):
+            return text.to(device)
+        return self.text_model(text).to(device)
+
+    @torch.no_grad()
+    def tokens2logits(self, token, text=None):
+        return self.transformer(token, text)
+
+    def _token_table(self):
+        """cat(raw codebook, mask_token): [n_embed + 1, 32] — un-normalised, as the reference (generate.py:149-154)."""
+        w = self.vqgan.quantize.embedding.weight
+        fp = (w.data_ptr(), w._version, self.mask_token.data_ptr(), self.mask_token._version)
+        if fp != self._table_fp:
+            self._table = torch.cat((w.detach().float(), self.mask_token.detach().float())).contiguous()
+            self._table_fp = fp
+        return self._table
+
+    @torch.no_grad()
+    def ids2tokens(self, ids):
+        table = self._token_table()
+        flat = ids.reshape(-1).to(torch.int64).contiguous()
+        out = torch.empty(flat.numel(), table.shape[1], device=ids.device, dtype=torch.float32)
+        ops.vq_gather(flat, table, False, out, None)
+        return out.reshape(*ids.shape, table.shape[1])
+
+    @torch.no_grad()
+    def sample(self, ids, mask_ratio, text=None, topk=1, temperature=1, decode=True, _noise=None):
+        """One MaskGIT step (generate.py:159-181) -> (ids, img).  `decode=False` skips the per-step
+        ViT decode (the reference decodes every step even when generate() discards the image, F9)."""
+        if not ids.is_cuda:
+            raise RuntimeError("paintmind_b200: CUDA only (no CPU fallback)")
+        B, N = ids.shape
+        dev = ids.device
+        table = self._token_table()
+        eng = self.transformer.engine()
+        ids = ids.to(torch.int64).contiguous().clone()
+        context = self._embed_text(text, dev) if text is not None else None
+        logits = eng.forward_from_ids(ids, table, context)                      # fp32 [B, N, V]
+        pred_ids = torch.empty(B, N, device=dev, dtype=torch.int64)
+        scores = torch.empty(B, N, device=dev, dtype=torch.float32)
+        if self._rng_seed is None:
+            self._rng_seed = torch.initial_seed()
+        self._rng_calls += 1
+        ops.maskgit_sample(logits.view(B * N, -1), topk=topk, temperature=temperature, ids=ids.view(-1),
+                           pred_ids=pred_ids.view(-1), scores=scores.view(-1), mask_id=self.mask_token_id,
+                           noise=None if _noise is None else _noise.reshape(B * N, -1),
+                           seed=self._rng_seed, offset=self._rng_calls)
+        img = self.vqgan.decode_from_indice(pred_ids) if decode else None
+        r = mask_ratio.item() if hasattr(mask_ratio, "item") else mask_ratio
+        num_token_masked = max(int(r * self.num_tokens), 1)
+        ops.maskgit_remask(scores, ids, num_token_masked, self.mask_token_id)
+        self._last_pred_ids, self._last_scores, self._last_logits = pred_ids, scores, logits
+        return ids, img
+
+    @torch.no_grad()
+    def generate(self, text, timesteps=18, temperature=1.0, topk=5, save_interval=2):
+        """MaskGIT iterative decoding (generate.py:183-198) -> list of CPU image tensors."""
+        dev = self.mask_token.device
+        B = len(text)
+        imgs = []
+        context = self._embed_text(text, dev)
+        ids = torch.full((B, self.num_tokens), self.mask_token_id, dtype=torch.long, device=dev)
+        for step in range(timesteps):
+            progress = (step + 1) / timesteps
+            masked_r = mask_schedule(progress)
+            cur_temp = temperature * (1 - step / timesteps)
+            keep = (step % save_interval == 0)
+            ids, img = self.sample(ids, mask_ratio=masked_r, text=context, topk=topk, temperature=cur_temp, decode=keep)
+            if keep:
+                imgs.append(img.cpu())
+        return imgs

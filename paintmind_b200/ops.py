@@ -13,6 +13,29 @@ from . import _lib
 from ._lib import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH  # noqa: F401
 
 
+# Optional per-launch timing (bench.py): when PROFILE is a dict, every op records CUDA events on the
+# launching stream around its kernel launch(es):  PROFILE[key] -> list of (start, end) events.
+PROFILE = None
+LAUNCHES = 0          # kernels launched through this module (bench.py's gpu_launches)
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(start, key, nkernels=1):
+    global LAUNCHES
+    LAUNCHES += nkernels
+    if start is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        PROFILE.setdefault(key, []).append((start, ev))
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -43,7 +66,9 @@ def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, o
     args.pos_rows = pos.shape[0] if pos is not None else 0
     args.out_mode, args.swiglu, args.bn = out_mode, int(bool(swiglu)), bn
     args.patch, args.channels, args.grid, args.max_ctas = patch, channels, grid, max_ctas
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_gemm_bf16(C.byref(args), _stream()), "pm_gemm_bf16")
+    _prof_end(t0, ("gemm", args.M, args.N, args.K, bool(swiglu), res is not None, stats is not None, out_mode))
     return out
 
 
@@ -56,7 +81,9 @@ def attention(q, k, v, o, heads, scale):
     args.bsq, args.bsk, args.bsv, args.bso = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
     args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
     args.scale = float(scale)
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_attn_fwd(C.byref(args), _stream()), "pm_attn_fwd")
+    _prof_end(t0, ("attention", args.B, args.H, args.Nq, args.Nk))
     return o
 
 
@@ -67,8 +94,10 @@ def vq_codebook_prep(E, en=None, packed=None):
         en = torch.empty(n_e, e_dim, device=E.device, dtype=torch.float32)
     if packed is None:
         packed = torch.empty(n_e, 2 * e_dim, device=E.device, dtype=torch.bfloat16)
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_vq_codebook_prep(_ptr(E), n_e, e_dim, _ptr(en), _ptr(packed), _stream()),
                "pm_vq_codebook_prep")
+    _prof_end(t0, ("vq_codebook_prep", n_e))
     return en, packed
 
 
@@ -82,27 +111,35 @@ def vq_forward(z2d, en, packed, *, idx, zq=None, zq_split=None, sse=None, hist=N
     args.sse, args.hist = _ptr(sse), _ptr(hist)
     args.ldz = z2d.stride(0)
     args.M, args.n_e, args.e_dim, args.splits = z2d.shape[0], en.shape[0], en.shape[1], splits
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_vq_fwd(C.byref(args), _stream()), "pm_vq_fwd")
+    _prof_end(t0, ("vq_forward", args.M, args.n_e), 2 if (splits != 1 and args.M < 150000) else 1)
 
 
 def vq_gather(idx, table, normalize, out=None, out_split=None):
     _require_cuda(idx, table)
     M = idx.numel()
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_vq_gather(_ptr(idx), M, table.shape[0], table.shape[1], _ptr(table), int(normalize),
                                         _ptr(out), _ptr(out_split), _stream()), "pm_vq_gather")
+    _prof_end(t0, ("vq_gather", M))
 
 
 def split_rows32(src2d, out_split):
     _require_cuda(src2d, out_split)
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_split_rows32(_ptr(src2d), src2d.stride(0), src2d.shape[0], _ptr(out_split), _stream()),
                "pm_split_rows32")
+    _prof_end(t0, ("split_rows32", src2d.shape[0]))
     return out_split
 
 
 def patchify8(img, out):
     _require_cuda(img, out)
     B, Cc, H, W = img.shape
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_patchify8(_ptr(img), _ptr(out), B, Cc, H, W, _stream()), "pm_patchify8")
+    _prof_end(t0, ("patchify8", B))
     return out
 
 
@@ -110,5 +147,40 @@ def layernorm(x, *, gamma=None, beta=None, y=None, stats=None, eps=1e-5):
     """y is None -> stats only; else y = LN(x) (and stats of y if given)."""
     _require_cuda(x)
     M, D = x.shape
+    t0 = _prof_begin()
     _lib.check(_lib.load().pm_layernorm(_ptr(x), x.stride(0), M, D, float(eps), _ptr(gamma), _ptr(beta), _ptr(y),
                                         y.stride(0) if y is not None else 0, _ptr(stats), _stream()), "pm_layernorm")
+    _prof_end(t0, ("layernorm" if y is not None else "ln_stats", M, D))
+
+
+def maskgit_sample(logits2d, *, topk, temperature, ids=None, pred_ids, scores, mask_id, noise=None, seed=0, offset=0):
+    """Fused top-k + gumbel arg-max + mask fill + confidence (generate.py:163-173) over fp32 logits [M, V]."""
+    _require_cuda(logits2d, pred_ids, scores)
+    a = _lib.MaskgitSampleArgs()
+    a.logits, a.noise, a.ids, a.pred_ids, a.scores = _ptr(logits2d), _ptr(noise), _ptr(ids), _ptr(pred_ids), _ptr(scores)
+    a.ld = logits2d.stride(0)
+    a.ld_noise = noise.stride(0) if noise is not None else 0
+    a.mask_id, a.seed, a.offset = int(mask_id), int(seed) & (2 ** 64 - 1), int(offset)
+    a.M, a.V, a.topk, a.temperature = logits2d.shape[0], logits2d.shape[1], int(topk), float(temperature)
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_maskgit_sample(C.byref(a), _stream()), "pm_maskgit_sample")
+    _prof_end(t0, ("maskgit_sample", a.M, a.V))
+
+
+def maskgit_remask(scores2d, ids2d, k, mask_id):
+    """ids.scatter(1, scores.topk(k).indices, mask_id) (generate.py:177-179), in place on ids."""
+    _require_cuda(scores2d, ids2d)
+    B, N = scores2d.shape
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_maskgit_remask(_ptr(scores2d), _ptr(ids2d), B, N, int(k), int(mask_id), _stream()),
+               "pm_maskgit_remask")
+    _prof_end(t0, ("maskgit_remask", B, N))
+
+
+def cast_bf16(src, dst):
+    """fp32 -> bf16 copy (numel % 8 == 0)."""
+    _require_cuda(src, dst)
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "pm_cast_f32_bf16")
+    _prof_end(t0, ("cast_bf16", src.numel()))
+    return dst

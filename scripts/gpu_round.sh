@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU session: tests, bench, launch list, ncu captures of the top kernels.  Outputs -> gpurun_out/
+set -u
+mkdir -p gpurun_out
+TAG=${1:-r1}
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/${TAG}_pytest_gpu.txt
+cat gpurun_out/${TAG}_pytest_gpu.txt
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 270 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+tail -2 gpurun_out/${TAG}_ncu_bench.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel.*Lb1 -s 16 -c 1 -o gpurun_out/${TAG}_swiglu -f \
+    python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_swiglu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 16 -c 1 -o gpurun_out/${TAG}_attn -f \
+    python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_attn.log 2>&1
+ls -la gpurun_out/
