@@ -1,0 +1,106 @@
+"""Host-side logic that needs no GPU: config / factory surface, state_dict contract, weight repacking algebra."""
+import numpy as np
+import pytest
+import torch
+
+import paintmind_b200 as pm
+from paintmind_b200.config import Config, ver2cfg
+from paintmind_b200.engine import fold_layernorm, pack_swiglu_w12, pack_w3
+from paintmind_b200.modules.mlp import swiglu_hidden
+from paintmind_b200.utils import synthetic
+
+
+def test_config_roundtrip(tmp_path):
+    c = Config(ver2cfg["vit-s-vqgan"])
+    assert c.n_embed == 8192 and c.embed_dim == 32 and c.beta == 0.25
+    assert c.enc["dim"] == 512 and c.enc["depth"] == 8 and c.dec["out_channels"] == 3
+    p = tmp_path / "c.json"
+    c.to_json(p)
+    d = Config()
+    d.from_json(p)
+    assert d.to_dict() == c.to_dict()
+    assert swiglu_hidden(2048) == 1368 and swiglu_hidden(4096) == 2736          # modules/mlp.py:53
+
+
+def test_factory_errors_match_reference():
+    with pytest.raises(KeyError):
+        pm.create_model(arch="vqgan", version="nope", pretrained=False)          # ver2cfg[version] (factory.py:7)
+    with pytest.raises(ValueError, match="failed to load arch named foo"):
+        pm.create_model(arch="foo", version="vit-s-vqgan", pretrained=False)     # factory.py:14
+
+
+def test_vqmodel_state_dict_contract():
+    """222 tensors, same keys/shapes as the reference VQModel; strict load works."""
+    m = pm.create_model(arch="vqgan", version="vit-s-vqgan", pretrained=False)
+    sd = m.state_dict()
+    assert len(sd) == 222 and sum(v.numel() for v in sd.values()) == 52_032_992
+    assert sd["encoder.to_patch_embedding.0.weight"].shape == (512, 3, 8, 8)
+    assert sd["encoder.transformer.layers.7.ffnet.w12.weight"].shape == (2736, 512)
+    assert sd["decoder.transformer.layers.0.attn1.to_out.0.bias"].shape == (512,)
+    assert sd["decoder.proj.weight"].shape == (192, 512) and sd["quantize.embedding.weight"].shape == (8192, 32)
+    assert "encoder.to_patch_embedding.0.bias" not in sd and "encoder.transformer.layers.0.attn1.to_q.bias" not in sd
+    syn = synthetic.make_vqgan_state_dict(ver2cfg["vit-s-vqgan"], seed=0)
+    assert set(syn) == set(sd) and all(syn[k].shape == sd[k].shape for k in sd)
+    res = m.load_state_dict(syn, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_cpu_model_fails_loudly():
+    """No CPU fallback: the product path raises instead of computing on the host."""
+    m = pm.create_model(arch="vqgan", version="vit-tiny-test", pretrained=False).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.encode(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.quantize(torch.zeros(1, 4, 32))
+
+
+def test_fold_layernorm_identity():
+    g = torch.Generator().manual_seed(0)
+    K, N, M = 64, 48, 33
+    W, b = torch.randn(N, K, generator=g).double(), torch.randn(N, generator=g).double()
+    gamma, beta = (torch.rand(K, generator=g) + 0.5).double(), torch.randn(K, generator=g).double()
+    x = torch.randn(M, K, generator=g).double() * 3 + 1
+    Wf, colsum, bias = fold_layernorm(W, b, gamma, beta)
+    mu = x.mean(1, keepdim=True)
+    rstd = (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    folded = rstd * (x @ Wf.double().t() - mu * colsum.double()[None]) + bias.double()[None]
+    ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5) @ W.t() + b
+    # only the bf16 rounding of W' separates the two
+    ref_bf = ((x - mu) * rstd) @ Wf.double().t() + (W @ beta + b)[None]
+    torch.testing.assert_close(folded, ref_bf, atol=2e-5, rtol=0)   # colsum / bias are kept in fp32
+    assert (folded - ref).abs().max() < 0.15
+
+
+def test_swiglu_repack_layout_and_padding():
+    g = torch.Generator().manual_seed(1)
+    K, h = 32, 200                                   # hidden 200 -> padded 256 = 2 tiles
+    w12, b12 = torch.randn(2 * h, K, generator=g), torch.randn(2 * h, generator=g)
+    ones, zeros = torch.ones(K), torch.zeros(K)
+    Wp, cs, bp, hp = pack_swiglu_w12(w12, b12, ones, zeros)
+    assert hp == 256 and Wp.shape == (512, K) and bp.shape == (512,)
+    for t in range(2):
+        lo, hi = t * 128, min((t + 1) * 128, h)
+        n = hi - lo
+        torch.testing.assert_close(Wp[t * 256:t * 256 + n].float(), w12[lo:hi].bfloat16().float())            # gate rows
+        torch.testing.assert_close(Wp[t * 256 + 128:t * 256 + 128 + n].float(), w12[h + lo:h + hi].bfloat16().float())  # value rows
+        torch.testing.assert_close(bp[t * 256:t * 256 + n], b12[lo:hi])
+        torch.testing.assert_close(bp[t * 256 + 128:t * 256 + 128 + n], b12[h + lo:h + hi])
+    assert float(Wp[256 + 72:256 + 128].abs().max()) == 0 and float(bp[256 + 72:256 + 128].abs().max()) == 0   # padding
+    w3 = torch.randn(16, h, generator=g)
+    w3p = pack_w3(w3, hp)
+    assert w3p.shape == (16, 256) and float(w3p[:, h:].abs().max()) == 0
+    # emulate the kernel epilogue on the packed layout and compare with the reference SwiGLU (mlp.py:27-31)
+    x = torch.randn(5, K, generator=g)
+    acc = x.bfloat16().float() @ Wp.float().t() + bp
+    hid = torch.cat([torch.nn.functional.silu(acc[:, t * 256:t * 256 + 128]) * acc[:, t * 256 + 128:(t + 1) * 256] for t in range(2)], 1)
+    out = hid @ w3p.float().t()
+    x12 = x.bfloat16().float() @ w12.bfloat16().float().t() + b12
+    ref = (torch.nn.functional.silu(x12[:, :h]) * x12[:, h:]) @ w3.bfloat16().float().t()
+    torch.testing.assert_close(out, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_pipeline_surface_and_schedule():
+    from paintmind_b200.generate import mask_schedule
+    ks = [max(int(mask_schedule((s + 1) / 12) * 1024), 1) for s in range(12)]
+    assert ks == [1015, 989, 946, 886, 812, 724, 623, 512, 391, 265, 133, 1]      # SURVEY.md §3.3 probe
+    assert isinstance(mask_schedule(0.5), np.floating)
