@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+if os.environ.get("PM_DEBUG"):
+    NVCC_FLAGS.append("-DPM_MBAR_PRINTF")     # print which mbarrier timed out before trapping
 
 
 def _nvcc() -> str:

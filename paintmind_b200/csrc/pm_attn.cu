@@ -7,26 +7,29 @@
 // column h*64) through 3-D TMA tensor maps, so no '(b h) n d' rearrange is ever materialised;
 // O is written token-major, ready for the to_out GEMM.
 //
-// One CTA per (128-query tile, head, batch); two CTAs co-reside per SM so that one CTA's softmax
-// overlaps the other's MMAs.  Per CTA (192 threads):
-//   warp 0 lane 0 : TMA producer (Q once; K/V tiles of 128 keys in a 2-stage ring)
-//   warp 1 lane 0 : MMA issuer   S = Q K^T (SS, 128x128x64) ;  O += P V (TS: P from TMEM,
-//                                V as MN-major smem operand, 128x64x128)
-//   warps 2..5    : softmax, one thread per query row: online max / sum in fp32 with lazy
-//                   rescaling of the TMEM-resident O accumulator, P written back over S as bf16.
+// One CTA per (256-query block, head, batch), one CTA per SM.  384 threads (register file rebalanced
+// with setmaxnreg: 216 per softmax thread, 64 for the TMA / MMA warpgroup):
+//   warps 0-3 / 4-7 : softmax warpgroup 0 / 1 — one thread per query row of Q tile 0 / 1:
+//                     fp32 online max / sum with lazy rescaling of the TMEM-resident O accumulator,
+//                     exp2 on the pre-scaled scores, P written back over S as packed bf16
+//   warp 8 lane 0   : TMA producer — both Q tiles once, K and V tiles of 128 keys in 3-stage rings
+//   warp 9 lane 0   : MMA issuer   — S_t = Q_t K^T (SS, 128x128x64) and O_t += P_t V (TS: P from
+//                     TMEM, V as MN-major smem operand, 128x64x128), interleaved between the two
+//                     Q tiles so the tensor core works on one tile while the other is in softmax
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); P_t aliases S_t[0,64).
 #include "pm_common.cuh"
 #include "pm_kernels.h"
 
 namespace pm {
 
-constexpr int AT_BM = 128;      // queries per CTA
+constexpr int AT_BM = 128;      // queries per tile (two tiles per CTA)
 constexpr int AT_BN = 128;      // keys per tile
 constexpr int AT_D = 64;        // head dim
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;   // 16 KB (Q, K and V tiles alike)
-constexpr int AT_KV_STAGES = 2;
-constexpr int AT_THREADS = 192;
-constexpr int AT_TMEM_COLS = 256;             // S: [0,128)  O: [128,192)
-constexpr int AT_SMEM_BYTES = 1024 + (1 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256;
+constexpr int AT_KV_STAGES = 3;
+constexpr int AT_THREADS = 384;            // 3 warpgroups: softmax 0, softmax 1, {TMA, MMA, 2 idle warps}
+constexpr int AT_TMEM_COLS = 512;
+constexpr int AT_SMEM_BYTES = 1024 + (2 + 2 * AT_KV_STAGES) * AT_TILE_BYTES + 256;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -34,45 +37,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
             const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smQ = smem;
-  uint8_t* smK = smem + AT_TILE_BYTES;
-  uint8_t* smV = smK + AT_KV_STAGES * AT_TILE_BYTES;
+  uint8_t* smQ = smem;                                       // [2][16 KB]
+  uint8_t* smK = smem + 2 * AT_TILE_BYTES;                   // [AT_KV_STAGES][16 KB]
+  uint8_t* smV = smK + AT_KV_STAGES * AT_TILE_BYTES;         // [AT_KV_STAGES][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smV + AT_KV_STAGES * AT_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                 // [2]
-  uint64_t* kv_empty = bars + 3;                // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* q_full = bars;                                   // [1]
+  uint64_t* k_full = bars + 1;                               // [3]
+  uint64_t* k_empty = k_full + AT_KV_STAGES;                 // [3]
+  uint64_t* v_full = k_empty + AT_KV_STAGES;                 // [3]
+  uint64_t* v_empty = v_full + AT_KV_STAGES;                 // [3]
+  uint64_t* s_full = v_empty + AT_KV_STAGES;                 // [2]
+  uint64_t* p_full = s_full + 2;                             // [2]
+  uint64_t* o_full = p_full + 2;                             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int n_kv_tiles = (p.Nk + AT_BN - 1) / AT_BN;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Nk + AT_BN - 1) / AT_BN;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
     mbar_init(q_full, 1);
     for (int i = 0; i < AT_KV_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);      // one arrival per softmax warp
-    mbar_init(o_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);      // one arrival per softmax warp of the group
+      mbar_init(&o_full[t], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, AT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -80,127 +89,178 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
 
-  if (warp == 0) {
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 8) {
+    // ===================================== TMA producer ======================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-      tma_load_3d(smQ, &tmQ, q_full, h * AT_D, qt * AT_BM, b);
-      for (int j = 0; j < n_kv_tiles; ++j) {
+      mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
+      tma_load_3d(smQ, &tmQ, q_full, h * AT_D, qb * 2 * AT_BM, b);
+      tma_load_3d(smQ + AT_TILE_BYTES, &tmQ, q_full, h * AT_D, qb * 2 * AT_BM + AT_BM, b);
+      for (int j = 0; j < n_kv; ++j) {
         const int st = j % AT_KV_STAGES;
-        mbar_wait(&kv_empty[st], ((j / AT_KV_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
-        tma_load_3d(smK + st * AT_TILE_BYTES, &tmK, &kv_full[st], h * AT_D, j * AT_BN, b);
-        tma_load_3d(smV + st * AT_TILE_BYTES, &tmV, &kv_full[st], h * AT_D, j * AT_BN, b);
+        const uint32_t ph = ((j / AT_KV_STAGES) & 1) ^ 1;
+        mbar_wait(&k_empty[st], ph);
+        mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
+        tma_load_3d(smK + st * AT_TILE_BYTES, &tmK, &k_full[st], h * AT_D, j * AT_BN, b);
+        mbar_wait(&v_empty[st], ph);
+        mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
+        tma_load_3d(smV + st * AT_TILE_BYTES, &tmV, &v_full[st], h * AT_D, j * AT_BN, b);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
+    // ===================================== MMA issuer ========================================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);   // Q, K both K-major
       constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);    // P K-major (TMEM), V MN-major
-      mbar_wait(q_full, 0);
-      const uint64_t dq = umma_desc_sw128(smem_u32(smQ));
-      for (int j = 0; j < n_kv_tiles; ++j) {
-        const int st = j % AT_KV_STAGES;
-        mbar_wait(&kv_full[st], (j / AT_KV_STAGES) & 1);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(smK + st * AT_TILE_BYTES));
+      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 320};
+      const uint64_t dq[2] = {umma_desc_sw128(smem_u32(smQ)), umma_desc_sw128(smem_u32(smQ + AT_TILE_BYTES))};
+
+      auto issue_qk = [&](int t, int j) {
+        const uint64_t dk = umma_desc_sw128(smem_u32(smK + (j % AT_KV_STAGES) * AT_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) umma_ss(tmem_S, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
-        // softmax turns S into P (bf16, in place) and rescales O when the running max moved
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint64_t dv = umma_desc_sw128(smem_u32(smV + st * AT_TILE_BYTES));
+        for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS[t], dq[t] + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {
+        const uint64_t dv = umma_desc_sw128(smem_u32(smV + (j % AT_KV_STAGES) * AT_TILE_BYTES));
 #pragma unroll
         for (int kk = 0; kk < AT_BN / 16; ++kk) {
           // A: 16 keys = 8 TMEM columns of packed bf16;  B: 16 key rows x 128 B = 2048 B
-          umma_ts(tmem_O, tmem_S + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          umma_ts(tO[t], tS[t] + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[st]);
-        if (j == n_kv_tiles - 1) umma_commit(o_full);
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % AT_KV_STAGES;
+        const uint32_t ph = (j / AT_KV_STAGES) & 1;
+        const bool more = (j + 1 < n_kv);
+        const int st1 = (j + 1) % AT_KV_STAGES;
+        const uint32_t ph1 = ((j + 1) / AT_KV_STAGES) & 1;
+        mbar_wait(&v_full[st], ph);
+        // ---- tile 0 ----
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, j);
+        if (more) {
+          mbar_wait(&k_full[st1], ph1);
+          tc_fence_after();
+          issue_qk(0, j + 1);               // S0 is overwritten only after PV0(j) has consumed P0 (in-order pipe)
+        } else {
+          umma_commit(&o_full[0]);
+        }
+        // ---- tile 1 ----
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, j);
+        umma_commit(&v_empty[st]);
+        if (more) {
+          issue_qk(1, j + 1);
+          umma_commit(&k_empty[st1]);
+        } else {
+          umma_commit(&o_full[1]);
+        }
       }
     }
+    }
   } else {
-    const int q = warp & 3;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ===================================== softmax warpgroups ================================
+    const int t = warp >> 2;                       // Q tile / warpgroup 0 or 1
+    const int q = warp & 3;                        // TMEM lane quarter
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const float c = p.scale_log2;        // softmax scale * log2(e)
-    float m_used = -INFINITY;            // running max (scaled, log2 domain) the accumulators refer to
-    float l = 0.0f;                      // running sum of exp2(t - m_used)
+    const uint32_t tS = tmem_base + t * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+    const float c = p.scale_log2;                  // softmax scale * log2(e)
+    float m_used = -INFINITY;                      // running max (scaled, log2 domain) the accumulators refer to
+    float2 l2 = make_float2(0.0f, 0.0f);           // running sum of exp2(s*c - m_used), two partial lanes
 
-    for (int j = 0; j < n_kv_tiles; ++j) {
-      const int valid = min(AT_BN, p.Nk - j * AT_BN);
-      mbar_wait(s_full, j & 1);
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = p.Nk - j * AT_BN;          // >= 128 for full tiles
+      mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      // ---- pass 1: row max of this tile ----
+      // ---- whole score row into registers ----
+      uint32_t s[4][32];
+      tmem_ld_x32(tS + 0, s[0]);
+      tmem_ld_x32(tS + 32, s[1]);
+      tmem_ld_x32(tS + 64, s[2]);
+      tmem_ld_x32(tS + 96, s[3]);
+      tmem_ld_wait();
+      if (valid < AT_BN) {                         // ragged last key tile (e.g. 77 text tokens): mask the tail
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i >= valid) s[ch][i] = 0xff800000u;      // -inf
+      }
+      // ---- row max (3-input max) ----
       float mt = -INFINITY;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_S + lane_off + cc * 32, r);
-        tmem_ld_wait();
+      for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (cc * 32 + i < valid) ? __uint_as_float(r[i]) : -INFINITY;
-          mt = fmaxf(mt, s);
-        }
-      }
+        for (int i = 0; i < 32; i += 2) mt = fmaxf(mt, fmaxf(__uint_as_float(s[ch][i]), __uint_as_float(s[ch][i + 1])));
       const float m_new = fmaxf(m_used, mt * c);
       // lazy rescale: keep the stale max while it is within 2^8 of the true one (exact algebra,
-      // bounded magnitude); the decision is made per warp to keep TMEM traffic warp-uniform
+      // bounded magnitude); decided per warp to keep the TMEM traffic warp-uniform
       const bool need = (m_new - m_used) > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
         if (need) m_used = m_new;
-        l *= alpha;
+        l2.x *= alpha;
+        l2.y *= alpha;
         if (j > 0) {
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             uint32_t r[32];
-            tmem_ld_x32(tmem_O + lane_off + cc * 32, r);
+            tmem_ld_x32(tO + cc * 32, r);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_x32(tmem_O + lane_off + cc * 32, r);
+            tmem_st_x32(tO + cc * 32, r);
           }
         }
       }
-      // ---- pass 2: P = exp2(s*c - m_used) -> bf16, written over S (cols 16*cc .. 16*cc+15) ----
-      const float moff = m_used;
+      // ---- P = exp2(s*c - m_used) -> packed bf16 over S columns [0, 64) ----
+      const float2 cc2 = make_float2(c, c);
+      const float2 mm2 = make_float2(-m_used, -m_used);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_S + lane_off + cc * 32, r);
-        tmem_ld_wait();
+      for (int ch = 0; ch < 4; ++ch) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float s0 = (cc * 32 + i < valid) ? __uint_as_float(r[i]) : -INFINITY;
-          const float s1 = (cc * 32 + i + 1 < valid) ? __uint_as_float(r[i + 1]) : -INFINITY;
-          const float p0 = ex2_approx(fmaf(s0, c, -moff));
-          const float p1 = ex2_approx(fmaf(s1, c, -moff));
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          const float2 x = make_float2(__uint_as_float(s[ch][i]), __uint_as_float(s[ch][i + 1]));
+          const float2 a = __ffma2_rn(x, cc2, mm2);
+          const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+          l2 = __fadd2_rn(l2, e);
+          pk[i >> 1] = pack_bf16x2(e.x, e.y);
         }
-        tmem_st_x16(tmem_S + lane_off + cc * 16, pk);
+        tmem_st_x16(tS + ch * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[t]);
     }
 
-    // ---- epilogue: O / l -> bf16 -> swizzled smem (Q buffer) -> TMA store ----
-    mbar_wait(o_full, 0);
+    // ---- epilogue: O / l -> bf16 -> swizzled smem (this tile's Q buffer) -> TMA store ----
+    mbar_wait(&o_full[t], 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
-    uint8_t* stg = smQ + row_in_tile * 128;
+    const float inv_l = 1.0f / (l2.x + l2.y);
+    uint8_t* stg_base = smQ + t * AT_TILE_BYTES;
+    uint8_t* stg = stg_base + row_in_tile * 128;
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       uint32_t r[32];
-      tmem_ld_x32(tmem_O + lane_off + cc * 32, r);
+      tmem_ld_x32(tO + cc * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int jv = 0; jv < 4; ++jv) {
@@ -214,12 +274,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (warp == 2 && lane == 0) {
+    named_bar_sync(1 + t, 128);
+    if (q == 0 && lane == 0) {
       asm volatile(
           "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
           ::"l"(reinterpret_cast<uint64_t>(&tmO)),
-          "r"(smem_u32(smQ)), "r"(h * AT_D), "r"(qt * AT_BM), "r"(b)
+          "r"(smem_u32(stg_base)), "r"(h * AT_D), "r"(qb * 2 * AT_BM + t * AT_BM), "r"(b)
           : "memory");
       tma_store_commit();
       tma_store_wait_all<0>();
@@ -228,7 +288,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, AT_TMEM_COLS);
@@ -251,7 +311,7 @@ int pm_attn_launch(const AttnParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  dim3 grid((p.Nq + AT_BM - 1) / AT_BM, p.H, p.B);
+  dim3 grid((p.Nq + 2 * AT_BM - 1) / (2 * AT_BM), p.H, p.B);
   attn_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return static_cast<int>(cudaGetLastError());
 }

@@ -84,8 +84,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ffu) == 0 && clock64() - t0 > PM_MBAR_TIMEOUT_CYCLES) {
+#ifdef PM_MBAR_PRINTF
       printf("pm: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
              blockIdx.y, threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }

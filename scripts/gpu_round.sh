@@ -7,11 +7,18 @@ timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/${TA
 cat gpurun_out/${TAG}_pytest_gpu.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+if [ "${2:-full}" = "full" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 270 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bench.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel.*Lb1 -s 16 -c 1 -o gpurun_out/${TAG}_swiglu -f \
+# 4th gemm launch of a step = layer-0 w12 (SwiGLU epilogue); 2nd = qkv (LN fold)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 3 -c 1 -o gpurun_out/${TAG}_swiglu -f \
     python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_swiglu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 16 -c 1 -o gpurun_out/${TAG}_attn -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 1 -c 1 -o gpurun_out/${TAG}_qkv -f \
+    python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_qkv.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 2 -c 1 -o gpurun_out/${TAG}_attn -f \
     python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_attn.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:vq_main_kernel -s 1 -c 1 -o gpurun_out/${TAG}_vq -f \
+    python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_vq.log 2>&1
+fi
 ls -la gpurun_out/
