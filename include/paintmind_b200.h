@@ -53,6 +53,8 @@ const char* pm_error_string(int rc);  /* static string for PM_ERR_* / cudaError_
  *   swiglu       : out[:, j] = silu(v[:, gate j]) * v[:, value j]     (mlp.py:29-30), W rows packed per
  *                  256-row tile as 128 gate rows then 128 value rows (see pm_repack docs in DESIGN.md)
  *   res          : v += res[row, col] (bf16)                          (layers.py:55-56)
+ *   stats_out    : row sums / sums of squares of the final values, so that the NEXT projection can fold
+ *                  the following LayerNorm without a separate statistics pass over HBM
  * ------------------------------------------------------------------------------------------- */
 typedef struct pm_gemm_args {
   const void* a;        /* bf16 [M, K], leading dim lda                                        */
@@ -71,6 +73,14 @@ typedef struct pm_gemm_args {
   int32_t bn;           /* N tile: 0 = auto, else one of 32/64/128/192/256                     */
   int32_t patch, channels, grid; /* PM_OUT_UNPATCH: patch size (8), channels (3), tokens/side  */
   int32_t max_ctas;     /* 0 = one CTA per SM; >0 caps the persistent grid (tests)             */
+  int32_t stats_raw;    /* P > 0: `stats` is [M, P, 2] partial (sum x, sum x^2) pairs over the K columns, as written
+                           by `stats_out` of the GEMM that produced A; 0: `stats` is [M, 2] = (mean, rstd)     */
+  float ln_eps;         /* LayerNorm eps used with stats_raw (1e-5)                                    */
+  float* stats_out;     /* [M, P, 2] fp32 with P = 2 * ceil(N / bn): per-row partial (sum, sum of squares) of the
+                           OUTPUT, one pair per N-tile and epilogue warp group (PM_OUT_BF16, no swiglu) or NULL */
+  int32_t cta_group;    /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pairs: tcgen05.mma.cta_group::2
+                           on 256 x 256 tiles (needs bn == 256)                                        */
+  int64_t* debug;       /* optional [grid, 4] int64 stall counters of the MMA issuer (profiling aid) or NULL      */
 } pm_gemm_args;
 
 int pm_gemm_bf16(const pm_gemm_args* args, void* stream);

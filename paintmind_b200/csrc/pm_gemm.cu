@@ -13,44 +13,51 @@
 //   * fp32 row-major store (prev_quant, vqmodel.py:23) or un-patchify + clamp to NCHW fp32
 //     (stage1/layers.py:150 + vqmodel.py:30)
 //
-// Structure per CTA (192 threads, 1 CTA / SM, grid = min(#tiles, #SMs)):
+// Structure per CTA (320 threads, 1 CTA / SM, grid = min(#tiles, #SMs); optionally CTA pairs, see GemmCfg):
 //   warp 0 lane 0 : TMA producer  — A and W tiles (128B swizzle) into a STAGES-deep smem ring
 //   warp 1 lane 0 : MMA issuer    — tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM,
 //                                   two accumulator stages so the epilogue overlaps the next tile
-//   warps 2..5    : epilogue      — tcgen05.ld -> registers -> fused math -> swizzled smem
-//                                   staging -> TMA store (bf16 outputs); residual tiles are
-//                                   TMA-prefetched into the same staging buffers.
+//   warps 2..9    : epilogue      — two groups of four warps on alternating 64-column chunks:
+//                                   tcgen05.ld -> registers -> fused math -> swizzled smem staging ->
+//                                   TMA store (bf16 outputs); residual tiles are TMA-prefetched one
+//                                   chunk ahead into the staging buffer the result is stored from.
 #include "pm_common.cuh"
 #include "pm_kernels.h"
 
 namespace pm {
 
-constexpr int BM = 128;
+constexpr int BM = 128;                       // accumulator rows per CTA (UMMA M = 128, or 256 across a CTA pair)
 constexpr int BK = 64;
-constexpr int NSTG = 4;                       // epilogue staging buffers (128 rows x 128 B)
-constexpr int STG_BYTES = BM * 128;           // 16 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int STG_BYTES = BM * 128;           // one epilogue staging buffer: 128 rows x 128 B = 16 KB
+constexpr int GEMM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
 
-template <int BN>
+// CTA2 = true: two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 of 256 x BN x 16.  Each CTA stages its own
+// 128 rows of A and HALF of the W tile (BN/2 rows), which halves the W bytes every SM pulls through L2 and smem
+// (the 1-CTA kernel is bound by L2->SM bandwidth: 128x256 tiles need ~12 TB/s at 1 PFLOP/s).
+template <int BN, bool CTA2>
 struct GemmCfg {
+  static constexpr int NSTG_G = 2;            // epilogue staging buffers per epilogue warp group
+  static constexpr int NSTG = 2 * NSTG_G;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // 227 KB total: staging + column vectors + barriers leave this much for the ring
-  static constexpr int RING_BUDGET = 232448 - NSTG * STG_BYTES - 2 * BN * 4 - 1024 - 1024;
+  static constexpr int RING_BUDGET = 232448 - NSTG * STG_BYTES - 2 * BN * 4 - 256;
   static constexpr int STAGES_RAW = RING_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + NSTG * STG_BYTES + 2 * BN * 4 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NSTG * STG_BYTES + 2 * BN * 4 + 256;
 };
 
 struct TileCoord {
   int m0, n0;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(int tile, int n_tiles, int bn) {
+// bm = rows per tile (128, or 256 for a CTA pair), m_off = this CTA's row offset inside the tile
+__device__ __forceinline__ TileCoord tile_coord(int tile, int n_tiles, int bn, int bm, int m_off) {
   TileCoord t;
-  t.m0 = (tile / n_tiles) * BM;
+  t.m0 = (tile / n_tiles) * bm + m_off;
   t.n0 = (tile % n_tiles) * bn;
   return t;
 }
@@ -63,19 +70,23 @@ __device__ __forceinline__ float silu_f(float x) {
   return x * r;
 }
 
-template <int BN, int OUT_MODE, bool SWIGLU>
+template <int BN, int OUT_MODE, bool SWIGLU, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NSTG = Cfg::NSTG;
+  constexpr int NSTG_G = Cfg::NSTG_G;
+  constexpr int TILE_M = CTA2 ? 2 * BM : BM;
   constexpr int OUT_COLS = SWIGLU ? BN / 2 : BN;           // output columns per tile
   constexpr int CHUNKS = (OUT_COLS + 63) / 64;             // 64-column output chunks per tile
   static_assert(!SWIGLU || (BN % 128 == 0), "SwiGLU tiles need BN multiple of 128");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled TMA / UMMA tiles need a 1024-byte aligned base
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* smC = smem + STAGES * Cfg::STAGE_BYTES;
@@ -85,40 +96,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint64_t* res_bar = tempty_bar + 2;           // [NSTG]
+  uint64_t* res_bar = tempty_bar + 2;           // [2 groups][NSTG_G]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NSTG);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
   const bool has_res = (p.res != nullptr);
+  // persistent schedule: a CTA (or CTA pair) walks tiles first, first + stride, ...
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int first_tile = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_stride = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int m_off = static_cast<int>(rank) * BM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (OUT_MODE == OUT_BF16) tma_prefetch_desc(&tmOut);
     if (has_res) tma_prefetch_desc(&tmRes);
+    for (int i = 0; i < NSTG; ++i) mbar_init(&res_bar[i], 1);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);   // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], CTA2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
-    for (int i = 0; i < NSTG; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // peer barriers initialised before any remote arrive / 2-SM TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -127,107 +149,170 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(tile, n_tiles, BN);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        const TileCoord tc = tile_coord(tile, n_tiles, BN, TILE_M, m_off);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, tc.m0);
-          tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, tc.n0);
+          if (CTA2) {
+            // both CTAs load their own A rows and their half of the W tile; all bytes are credited to the
+            // leader's full barrier, which alone is armed (with the pair's total)
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, tc.m0);
+            tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, tc.n0 + static_cast<int>(rank) * Cfg::B_ROWS);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, tc.m0);
+            tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, tc.n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {        // in a CTA pair only the leader issues MMAs
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // optional stall accounting (p.debug != nullptr): cycles the issuer spent waiting for accumulators / operands
+      long long t_acc = 0, t_opr = 0;
+      const long long t_begin = clock64();
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        long long t0 = clock64();
         mbar_wait(&tempty_bar[as], aphase ^ 1);
+        t_acc += clock64() - t0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          t0 = clock64();
           mbar_wait(&full_bar[stage], phase);
+          t_opr += clock64() - t0;
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(smA + stage * Cfg::A_BYTES));
           const uint64_t db = umma_desc_sw128(smem_u32(smB + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in 16 B units
-            umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CTA2) umma_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+          if (CTA2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);        // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CTA2) umma_commit_2sm(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+      if (p.debug != nullptr) {
+        long long* d = p.debug + 4 * static_cast<size_t>(blockIdx.x);
+        d[0] = t_acc; d[1] = t_opr; d[2] = clock64() - t_begin; d[3] = k_blocks;
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ============================
+    // =============================== epilogue (warps 2..9) ============================
+    // Two groups of four warps (one warp per TMEM lane quarter each).  Group g drains the 64-column output
+    // chunks c = g, g+2, ... of every tile, so each SM sub-partition always has two epilogue warps whose
+    // TMEM / shared / global latencies overlap.  Each group owns NSTG_G staging buffers, two named barriers
+    // and a leader thread that issues the TMA stores.
+    const int ew = warp - 2;                    // 0..7
+    const int grp = ew >> 2;                    // chunk parity this warp works on
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
-    const int et = (warp - 2) * 32 + lane;      // 0..127 epilogue thread id
+    const int et = ew * 32 + lane;              // 0..255 epilogue thread id
     const int row_in_tile = q * 32 + lane;
-    const bool leader = (warp == 2 && lane == 0);
+    const bool leader = ((ew & 3) == 0 && lane == 0);
     const uint32_t tmem_lane = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t bar_free = 2 + 2 * grp, bar_full = 3 + 2 * grp;     // named barriers of this group (128 threads)
+    uint8_t* stage_base = smC + grp * NSTG_G * STG_BYTES;
+    const uint32_t tempty_leader = CTA2 ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;   // leader CTA's tempty_bar[0]
 
-    const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const int total_chunks = my_tiles * CHUNKS;
-
-    // residual prefetch: chunk g lives in staging buffer g % NSTG
+    const int my_tiles = first_tile < total_tiles ? (total_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
+    constexpr int CPG0 = (CHUNKS + 1) / 2, CPG1 = CHUNKS / 2;      // chunks per tile of group 0 / 1
+    const int cpg = grp == 0 ? CPG0 : CPG1;
+    const int group_chunks = my_tiles * cpg;
+    // residual prefetch by TMA into the staging buffer the result will be stored from
     auto issue_res = [&](int g) {
-      const int ti = g / CHUNKS, c = g % CHUNKS;
-      const TileCoord tc = tile_coord(blockIdx.x + ti * gridDim.x, n_tiles, BN);
-      const int b = g % NSTG;
-      mbar_arrive_expect_tx(&res_bar[b], STG_BYTES);
-      tma_load_2d(smC + b * STG_BYTES, &tmRes, &res_bar[b], (SWIGLU ? tc.n0 / 2 : tc.n0) + c * 64, tc.m0);
+      const int ti = g / cpg, c = grp + 2 * (g % cpg);
+      const TileCoord rc = tile_coord(first_tile + ti * tile_stride, n_tiles, BN, TILE_M, m_off);
+      uint64_t* bar = &res_bar[grp * NSTG_G + g % NSTG_G];
+      mbar_arrive_expect_tx(bar, STG_BYTES);
+      tma_load_2d(stage_base + (g % NSTG_G) * STG_BYTES, &tmRes, bar, (SWIGLU ? rc.n0 / 2 : rc.n0) + c * 64, rc.m0);
     };
-    if (OUT_MODE == OUT_BF16 && has_res && leader) {
-      for (int g = 0; g < NSTG && g < total_chunks; ++g) issue_res(g);
-    }
+    if (OUT_MODE == OUT_BF16 && has_res && leader && group_chunks > 0) issue_res(0);
 
     int as = 0;
     uint32_t aphase = 0;
-    int g = 0;   // running chunk counter
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(tile, n_tiles, BN);
+    int gl = 0;   // chunks stored so far by this group (staging buffer = gl % NSTG_G)
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+      const TileCoord tc = tile_coord(tile, n_tiles, BN, TILE_M, m_off);
       const int row = tc.m0 + row_in_tile;
       const bool row_ok = row < p.M;
+      const int out_n0 = SWIGLU ? tc.n0 / 2 : tc.n0;
 
-      // per-tile column vectors -> smem
-      named_bar_sync(1, 128);
-      for (int i = et; i < BN; i += 128) {
+      // per-tile column vectors -> smem (all 8 warps)
+      named_bar_sync(1, 256);
+      for (int i = et; i < BN; i += 256) {
         const int col = tc.n0 + i;
         colvec[i] = (p.bias != nullptr && col < p.N) ? p.bias[col] : 0.0f;
         colvec[BN + i] = (p.colsum != nullptr && col < p.N) ? p.colsum[col] : 0.0f;
       }
       float mu = 0.0f, rstd = 1.0f;
       if (p.stats != nullptr && row_ok) {
-        const float2 st = *reinterpret_cast<const float2*>(p.stats + 2 * static_cast<size_t>(row));
+        const float2 st = p.stats_raw > 0 ? make_float2(0.0f, 1.0f) : *reinterpret_cast<const float2*>(p.stats + 2 * static_cast<size_t>(row));
         mu = st.x;
         rstd = st.y;
+        if (p.stats_raw > 0) {
+          // p.stats_raw partial (sum, sum of squares) pairs per row, written by the epilogue of the GEMM that
+          // produced A (one pair per N-tile and epilogue group); summed here in a fixed order -> deterministic
+          const float* sp = p.stats + 2 * static_cast<size_t>(p.stats_raw) * row;
+          float s1 = 0.0f, s2 = 0.0f;
+          for (int i = 0; i < p.stats_raw; ++i) {
+            const float2 t = *reinterpret_cast<const float2*>(sp + 2 * i);
+            s1 += t.x;
+            s2 += t.y;
+          }
+          const float inv_k = 1.0f / static_cast<float>(p.K);
+          mu = s1 * inv_k;
+          const float var = fmaxf(s2 * inv_k - mu * mu, 0.0f);
+          rstd = rsqrtf(var + p.ln_eps);
+        }
       }
-      const float nrmu = -rstd * mu;     // LN fold: rstd * (acc - mu * colsum) + bias == acc * rstd + (nrmu * colsum + bias)
+      float row_s1 = 0.0f, row_s2 = 0.0f;   // statistics of this thread's output columns (for the next LayerNorm)
+      const float nrmu = -rstd * mu;        // LN fold: rstd * (acc - mu * colsum) + bias == acc * rstd + (nrmu * colsum + bias)
       const float* pos_row = nullptr;
       if (p.pos != nullptr && row_ok) pos_row = p.pos + static_cast<size_t>(row % p.pos_rows) * p.ld_pos;
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + tmem_lane + as * BN;
 
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c, ++g) {
-        // ---- 64 output values of this thread's row for this chunk ----
-        float v[64];
+      for (int c = grp; c < CHUNKS; c += 2) {
+        const bool last_chunk = (c + 2 >= CHUNKS);
+        uint8_t* stg = nullptr;
+        if (OUT_MODE == OUT_BF16) {
+          if (has_res) {
+            // chunk gl-1's store has left its buffer: prefetch the residual of chunk gl+1 into it (a whole chunk
+            // ahead of its use); this chunk's residual was requested one chunk ago
+            if (leader) {
+              tma_store_wait_read<0>();
+              if (gl + 1 < group_chunks) issue_res(gl + 1);
+            }
+          } else {
+            // staging buffer free? (its previous TMA store has finished reading shared memory)
+            if (leader) tma_store_wait_read<NSTG_G - 1>();
+            named_bar_sync(bar_free, 128);
+          }
+          stg = stage_base + (gl % NSTG_G) * STG_BYTES + row_in_tile * 128;
+        }
         constexpr int HALVES = (OUT_COLS >= 64) ? 2 : 1;   // BN=32 tiles have a single 32-col half
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
           const int oc = c * 64 + h * 32;                   // output column inside the tile
+          float v[32];
           if (SWIGLU) {
             uint32_t rg[32], rv[32];
             tmem_ld_x32(tacc + oc, rg);
@@ -245,7 +330,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int t = 0; t < 4; ++t) {
                 const float a = fmaf(__uint_as_float(rg[j + t]), rstd, fmaf(nrmu, cgs[t], bgs[t]));
                 const float b = fmaf(__uint_as_float(rv[j + t]), rstd, fmaf(nrmu, cvs[t], bvs[t]));
-                v[h * 32 + j + t] = silu_f(a) * b;
+                v[j + t] = silu_f(a) * b;
               }
             }
           } else {
@@ -259,7 +344,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float bbs[4] = {bb.x, bb.y, bb.z, bb.w}, ccs[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t)
-                v[h * 32 + j + t] = fmaf(__uint_as_float(ra[j + t]), rstd, fmaf(nrmu, ccs[t], bbs[t]));
+                v[j + t] = fmaf(__uint_as_float(ra[j + t]), rstd, fmaf(nrmu, ccs[t], bbs[t]));
             }
             if (pos_row != nullptr) {
               const int col0 = tc.n0 + oc;
@@ -267,90 +352,99 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int j = 0; j < 32; j += 4) {
                 if (col0 + j < p.N) {
                   const float4 pe = *reinterpret_cast<const float4*>(pos_row + col0 + j);
-                  v[h * 32 + j] += pe.x; v[h * 32 + j + 1] += pe.y;
-                  v[h * 32 + j + 2] += pe.z; v[h * 32 + j + 3] += pe.w;
+                  v[j] += pe.x; v[j + 1] += pe.y; v[j + 2] += pe.z; v[j + 3] += pe.w;
+                }
+              }
+            }
+          }
+          if (last_chunk && h == HALVES - 1) {
+            // all TMEM reads of this accumulator stage by this warp are done -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CTA2) mbar_arrive_cluster(tempty_leader + as * 8);   // the leader's MMA thread owns the accumulators of both CTAs
+              else mbar_arrive(&tempty_bar[as]);
+            }
+          }
+
+          if (OUT_MODE == OUT_BF16) {
+            if (has_res && h == 0) mbar_wait(&res_bar[grp * NSTG_G + gl % NSTG_G], (gl / NSTG_G) & 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float* x = &v[j * 8];
+              uint4* slot = reinterpret_cast<uint4*>(stg + (((h * 4 + j) ^ (row_in_tile & 7)) << 4));
+              if (has_res) {
+                const uint4 r = *slot;
+                x[0] += bf16lo_to_f32(r.x); x[1] += bf16hi_to_f32(r.x);
+                x[2] += bf16lo_to_f32(r.y); x[3] += bf16hi_to_f32(r.y);
+                x[4] += bf16lo_to_f32(r.z); x[5] += bf16hi_to_f32(r.z);
+                x[6] += bf16lo_to_f32(r.w); x[7] += bf16hi_to_f32(r.w);
+              }
+              uint4 o;
+              o.x = pack_bf16x2(x[0], x[1]);
+              o.y = pack_bf16x2(x[2], x[3]);
+              o.z = pack_bf16x2(x[4], x[5]);
+              o.w = pack_bf16x2(x[6], x[7]);
+              *slot = o;
+              if (!SWIGLU && p.stats_out != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  row_s1 += x[e];
+                  row_s2 = fmaf(x[e], x[e], row_s2);
+                }
+              }
+            }
+          } else if (OUT_MODE == OUT_F32) {
+            if (row_ok) {
+              float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ld_out + tc.n0 + oc;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (tc.n0 + oc + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+            }
+          } else {  // OUT_UNPATCH: column = (p1 * P + p2) * C + ch  ->  out[b, ch, h*P + p1, w*P + p2]
+            if (row_ok) {
+              const int P = p.patch, C = p.channels, G = p.grid;   // G tokens per image side
+              const int tok = row % (G * G), bimg = row / (G * G);
+              const int th = tok / G, tw = tok % G;
+              const int S = G * P;                                  // image side
+              float* img = reinterpret_cast<float*>(p.out) + static_cast<size_t>(bimg) * C * S * S;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = tc.n0 + oc + j;
+                if (col < p.N) {
+                  const int ch = col % C, pp = col / C;
+                  const int p1 = pp / P, p2 = pp % P;
+                  img[(static_cast<size_t>(ch) * S + th * P + p1) * S + tw * P + p2] = fminf(fmaxf(v[j], -1.0f), 1.0f);
                 }
               }
             }
           }
         }
-        if (c == CHUNKS - 1) {
-          // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        }
 
         if (OUT_MODE == OUT_BF16) {
-          const int b = g % NSTG;
-          uint8_t* stg = smC + b * STG_BYTES + row_in_tile * 128;
-          if (has_res) {
-            mbar_wait(&res_bar[b], (g / NSTG) & 1);
-          } else {
-            if (leader) tma_store_wait_read<NSTG - 1>();
-            named_bar_sync(2, 128);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4* slot = reinterpret_cast<uint4*>(stg + ((j ^ (row_in_tile & 7)) << 4));
-            float* x = &v[j * 8];
-            if (has_res) {
-              const uint4 r = *slot;
-              x[0] += bf16lo_to_f32(r.x); x[1] += bf16hi_to_f32(r.x);
-              x[2] += bf16lo_to_f32(r.y); x[3] += bf16hi_to_f32(r.y);
-              x[4] += bf16lo_to_f32(r.z); x[5] += bf16hi_to_f32(r.z);
-              x[6] += bf16lo_to_f32(r.w); x[7] += bf16hi_to_f32(r.w);
-            }
-            uint4 o;
-            o.x = pack_bf16x2(x[0], x[1]);
-            o.y = pack_bf16x2(x[2], x[3]);
-            o.z = pack_bf16x2(x[4], x[5]);
-            o.w = pack_bf16x2(x[6], x[7]);
-            *slot = o;
-          }
           fence_proxy_async_smem();
-          named_bar_sync(3, 128);
+          named_bar_sync(bar_full, 128);
           if (leader) {
-            tma_store_2d(&tmOut, smC + b * STG_BYTES, (SWIGLU ? tc.n0 / 2 : tc.n0) + c * 64, tc.m0);
+            tma_store_2d(&tmOut, stage_base + (gl % NSTG_G) * STG_BYTES, out_n0 + c * 64, tc.m0);
             tma_store_commit();
-            if (has_res) {
-              // buffer of the previous chunk becomes free once its store has read smem;
-              // refill it with the residual tile NSTG chunks ahead
-              if (g >= 1 && g - 1 + NSTG < total_chunks) {
-                tma_store_wait_read<1>();
-                issue_res(g - 1 + NSTG);
-              }
-            }
           }
-        } else if (OUT_MODE == OUT_F32) {
-          if (row_ok) {
-            float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ld_out + tc.n0 + c * 64;
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              if (j < OUT_COLS && tc.n0 + c * 64 + j < p.N) {
-                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              }
-            }
-          }
-        } else {  // OUT_UNPATCH: column = (p1 * P + p2) * C + ch  ->  out[b, ch, h*P + p1, w*P + p2]
-          if (row_ok) {
-            const int P = p.patch, C = p.channels, G = p.grid;   // G tokens per image side
-            const int tok = row % (G * G), bimg = row / (G * G);
-            const int th = tok / G, tw = tok % G;
-            const int S = G * P;                                  // image side
-            float* img = reinterpret_cast<float*>(p.out) + static_cast<size_t>(bimg) * C * S * S;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const int col = tc.n0 + c * 64 + j;
-              if (j < OUT_COLS && col < p.N) {
-                const int ch = col % C, pp = col / C;
-                const int p1 = pp / P, p2 = pp % P;
-                const float x = fminf(fmaxf(v[j], -1.0f), 1.0f);
-                img[(static_cast<size_t>(ch) * S + th * P + p1) * S + tw * P + p2] = x;
-              }
-            }
-          }
+          ++gl;
         }
+      }
+      if (CHUNKS <= grp) {
+        // this group has no chunk in such a narrow tile: it still has to release the accumulator stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_cluster(tempty_leader + as * 8);
+          else mbar_arrive(&tempty_bar[as]);
+        }
+      }
+      if (OUT_MODE == OUT_BF16 && !SWIGLU && p.stats_out != nullptr && row_ok) {
+        // slot (n_tile, group) of this row: [M, 2 * n_tiles, 2] — no atomics, no zero-fill, fixed summation order
+        const int slot = (tile % n_tiles) * 2 + grp;
+        *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(row) * (2 * n_tiles) + slot) * 2) = make_float2(row_s1, row_s2);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -359,10 +453,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // no CTA may exit (or free TMEM) while its peer can still signal it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -380,69 +476,90 @@ int pm_num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int OUT_MODE, bool SWIGLU>
-static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, int OUT_MODE, bool SWIGLU, bool CTA2>
+static int launch_gemm(const GemmParams& p_in, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CTA2>;
   static_assert(Cfg::STAGES >= 2, "not enough shared memory for a pipeline");
+  GemmParams p = p_in;
   CUtensorMap tmA, tmB, tmOut, tmRes;
   int rc;
   if ((rc = pm_make_tmap_2d(&tmA, p.a, 2, p.M, p.K, p.lda, BM, BK)) != PM_OK) return rc;
-  if ((rc = pm_make_tmap_2d(&tmB, p.w, 2, p.N, p.K, p.ldw, BN, BK)) != PM_OK) return rc;
+  if ((rc = pm_make_tmap_2d(&tmB, p.w, 2, p.N, p.K, p.ldw, Cfg::B_ROWS, BK)) != PM_OK) return rc;
   const int out_cols = SWIGLU ? p.N / 2 : p.N;
   if (OUT_MODE == OUT_BF16) {
     if ((rc = pm_make_tmap_2d(&tmOut, p.out, 2, p.M, out_cols, p.ld_out, BM, 64)) != PM_OK) return rc;
   } else {
     tmOut = tmA;
   }
+  p.N_out = out_cols;
   if (p.res != nullptr) {
     if (OUT_MODE != OUT_BF16) return PM_ERR_INVALID;
     if ((rc = pm_make_tmap_2d(&tmRes, p.res, 2, p.M, out_cols, p.ld_res, BM, 64)) != PM_OK) return rc;
   } else {
     tmRes = tmA;
   }
-  auto kern = gemm_kernel<BN, OUT_MODE, SWIGLU>;
+  auto kern = gemm_kernel<BN, OUT_MODE, SWIGLU, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  constexpr int TILE_M = CTA2 ? 2 * BM : BM;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M, n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
-  int grid = tiles < pm_num_sms() ? tiles : pm_num_sms();
+  const int units = CTA2 ? pm_num_sms() / 2 : pm_num_sms();       // CTAs or CTA pairs that fit the machine
+  int grid = tiles < units ? tiles : units;
   if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmRes, p);
-  return static_cast<int>(cudaGetLastError());
+  if (!CTA2) {
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmRes, p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, p));
 }
 
 int pm_gemm_launch(const GemmParams& p, int bn, int out_mode, int swiglu, cudaStream_t stream) {
   if (p.a == nullptr || p.w == nullptr || p.out == nullptr || p.M <= 0 || p.N <= 0 || p.K <= 0)
     return PM_ERR_INVALID;
+  // CTA pairs (256 x 256 tiles) whenever there is enough work to fill the machine with them
+  const bool pair = p.cta_pair != 0 && bn == 256 && p.M >= 256;
   if (swiglu) {
     if (out_mode != OUT_BF16 || bn != 256 || (p.N % 256) != 0) return PM_ERR_INVALID;
-    return launch_gemm<256, OUT_BF16, true>(p, stream);
+    return pair ? launch_gemm<256, OUT_BF16, true, true>(p, stream) : launch_gemm<256, OUT_BF16, true, false>(p, stream);
   }
   if (out_mode == OUT_BF16) {
     switch (bn) {
-      case 256: return launch_gemm<256, OUT_BF16, false>(p, stream);
-      case 128: return launch_gemm<128, OUT_BF16, false>(p, stream);
-      case 64:  return launch_gemm<64, OUT_BF16, false>(p, stream);
+      case 256: return pair ? launch_gemm<256, OUT_BF16, false, true>(p, stream) : launch_gemm<256, OUT_BF16, false, false>(p, stream);
+      case 128: return launch_gemm<128, OUT_BF16, false, false>(p, stream);
+      case 64:  return launch_gemm<64, OUT_BF16, false, false>(p, stream);
       default:  return PM_ERR_INVALID;
     }
   }
   if (out_mode == OUT_F32) {
     switch (bn) {
-      case 32:  return launch_gemm<32, OUT_F32, false>(p, stream);
-      case 64:  return launch_gemm<64, OUT_F32, false>(p, stream);
-      case 128: return launch_gemm<128, OUT_F32, false>(p, stream);
-      case 256: return launch_gemm<256, OUT_F32, false>(p, stream);
+      case 32:  return launch_gemm<32, OUT_F32, false, false>(p, stream);
+      case 64:  return launch_gemm<64, OUT_F32, false, false>(p, stream);
+      case 128: return launch_gemm<128, OUT_F32, false, false>(p, stream);
+      case 256: return pair ? launch_gemm<256, OUT_F32, false, true>(p, stream) : launch_gemm<256, OUT_F32, false, false>(p, stream);
       default:  return PM_ERR_INVALID;
     }
   }
   if (out_mode == OUT_UNPATCH) {
     switch (bn) {
-      case 64:  return launch_gemm<64, OUT_UNPATCH, false>(p, stream);
-      case 192: return launch_gemm<192, OUT_UNPATCH, false>(p, stream);
+      case 64:  return launch_gemm<64, OUT_UNPATCH, false, false>(p, stream);
+      case 192: return launch_gemm<192, OUT_UNPATCH, false, false>(p, stream);
       default:  return PM_ERR_INVALID;
     }
   }

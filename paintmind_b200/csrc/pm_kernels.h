@@ -18,9 +18,15 @@ struct GemmParams {
   const void* res;
   int64_t lda, ldw, ld_out, ld_pos, ld_res;
   int M, N, K;
+  int N_out;          // output columns (N, or N/2 with SwiGLU); set by the launcher
   int pos_rows;
   int patch, channels, grid;
   int max_ctas;
+  float* stats_out;   // [M, 2] += (sum x, sum x^2) of the OUTPUT rows (OUT_BF16, non-SwiGLU), or nullptr
+  int stats_raw;      // 1: `stats` holds raw (sum, sum of squares) over K columns; 0: (mean, rstd)
+  float ln_eps;
+  long long* debug;   // optional [grid, 4] int64: MMA-issuer stall cycles (accumulator wait, operand wait, total, k_blocks)
+  int cta_pair;       // 1: use the cta_group::2 kernel (256-row tiles) when the tile shape allows it
 };
 
 struct AttnParams {

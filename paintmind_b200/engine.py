@@ -128,9 +128,41 @@ class _Workspace:
         return t
 
 
-def run_blocks(blocks, x, stats, B, N, ws, context_kv=None, ctx_len=0):
-    """Run packed transformer blocks in place on x [B*N, D] (bf16).  `stats` must hold the LayerNorm
-    statistics of x on entry and holds those of the final x on exit."""
+class _RowStats:
+    """LayerNorm statistics of the residual stream x [M, D].
+
+    A GEMM that writes x also writes, per row, P = 2 * ceil(D / bn) partial (sum, sum of squares) pairs
+    (`stats_out`, one per N-tile and epilogue warp group); the next LN-folded GEMM sums them in a fixed order and
+    converts to (mean, rstd) in its epilogue (`stats_raw = P`).  Two buffers are ping-ponged because a GEMM that
+    updates x in place reads the statistics of the old x while producing those of the new one.  Only `norm_pre`
+    (a real LayerNorm kernel) produces finished (mean, rstd) pairs (`stats_raw = 0`)."""
+
+    def __init__(self, ws, M, D, dev):
+        self.parts = ops.stats_parts(D)
+        self.bufs = [ws.get("stats_a", (M, 2 * self.parts), torch.float32, dev),
+                     ws.get("stats_b", (M, 2 * self.parts), torch.float32, dev)]
+        self.fin = ws.get("stats_fin", (M, 2), torch.float32, dev)
+        self.cur = 0
+        self.raw = self.parts
+
+    def finished(self):
+        """(mean, rstd) buffer to be filled by the LayerNorm kernel; becomes current."""
+        self.raw = 0
+        return self.fin
+
+    def consume(self):
+        return dict(stats=self.fin if self.raw == 0 else self.bufs[self.cur], stats_raw=self.raw)
+
+    def produce(self):
+        """Buffer for the producing GEMM's partial sums; becomes current."""
+        self.cur ^= 1
+        self.raw = self.parts
+        return self.bufs[self.cur]
+
+
+def run_blocks(blocks, x, st, B, N, ws, context_kv=None, ctx_len=0):
+    """Run packed transformer blocks in place on x [B*N, D] (bf16).  `st` (_RowStats) must describe the
+    current x on entry and describes the final x on exit."""
     M, D = x.shape
     dev = x.device
     for li, blk in enumerate(blocks):
@@ -138,30 +170,27 @@ def run_blocks(blocks, x, stats, B, N, ws, context_kv=None, ctx_len=0):
         qkv = ws.get("qkv", (M, 3 * inner), torch.bfloat16, dev)
         ao = ws.get("ao", (M, inner), torch.bfloat16, dev)
         # x = attn1(norm1(x)) + x
-        ops.gemm(x, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, stats=stats)
+        ops.gemm(x, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, **st.consume())
         q3 = qkv.view(B, N, 3 * inner)
         ops.attention(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), blk.heads, blk.scale)
-        ops.gemm(ao, blk.w_o, x, bias=blk.b_o, res=x)
-        ops.layernorm(x, stats=stats)
+        ops.gemm(ao, blk.w_o, x, bias=blk.b_o, res=x, stats_out=st.produce())
         if blk.cross:
             # x = attn2(norm2(x), context) + x
             q2 = ws.get("q2", (M, inner), torch.bfloat16, dev)
-            ops.gemm(x, blk.w_q2, q2, bias=blk.b_q2, colsum=blk.cs_q2, stats=stats)
+            ops.gemm(x, blk.w_q2, q2, bias=blk.b_q2, colsum=blk.cs_q2, **st.consume())
             if context_kv is not None:
                 kv = context_kv[li]
                 kv3 = kv.view(B, ctx_len, 2 * inner)
             else:
                 kv = ws.get("kv2", (M, 2 * inner), torch.bfloat16, dev)
-                ops.gemm(x, blk.w_kv2_self, kv, bias=blk.b_kv2_self, colsum=blk.cs_kv2_self, stats=stats)
+                ops.gemm(x, blk.w_kv2_self, kv, bias=blk.b_kv2_self, colsum=blk.cs_kv2_self, **st.consume())
                 kv3 = kv.view(B, N, 2 * inner)
             ops.attention(q2.view(B, N, inner), kv3[..., :inner], kv3[..., inner:], ao.view(B, N, inner), blk.heads, blk.scale2)
-            ops.gemm(ao, blk.w_o2, x, bias=blk.b_o2, res=x)
-            ops.layernorm(x, stats=stats)
+            ops.gemm(ao, blk.w_o2, x, bias=blk.b_o2, res=x, stats_out=st.produce())
         # x = ffnet(norm(x)) + x
         h = ws.get("h", (M, blk.hp), torch.bfloat16, dev)
-        ops.gemm(x, blk.w_12, h, bias=blk.b_12, colsum=blk.cs_12, stats=stats, swiglu=True)
-        ops.gemm(h, blk.w_3, x, bias=blk.b_3, res=x)
-        ops.layernorm(x, stats=stats)
+        ops.gemm(x, blk.w_12, h, bias=blk.b_12, colsum=blk.cs_12, swiglu=True, **st.consume())
+        ops.gemm(h, blk.w_3, x, bias=blk.b_3, res=x, stats_out=st.produce())
     return x
 
 
@@ -248,11 +277,11 @@ class Stage1Engine:
         patches = ws.get("patches", (M, C * 64), torch.bfloat16, dev)
         x0 = ws.get("x0", (M, D), torch.bfloat16, dev)
         x = ws.get("x", (M, D), torch.bfloat16, dev)
-        stats = ws.get("stats", (M, 2), torch.float32, dev)
+        st = _RowStats(ws, M, D, dev)
         ops.patchify8(img, patches)
         ops.gemm(patches, self.w_pe, x0, pos=self.enc_pos)                        # conv-as-GEMM + position embedding
-        ops.layernorm(x0, gamma=self.pre_g, beta=self.pre_b, y=x, stats=stats)    # norm_pre
-        run_blocks(self.enc_blocks, x, stats, B, N, ws)
+        ops.layernorm(x0, gamma=self.pre_g, beta=self.pre_b, y=x, stats=st.finished())   # norm_pre (+ stats of its output)
+        run_blocks(self.enc_blocks, x, st, B, N, ws)
         return x.view(B, N, D)
 
     def encode(self, img):
@@ -277,15 +306,15 @@ class Stage1Engine:
         return z.view(B, N, -1)
 
     # -- decoder -------------------------------------------------------------------------------
-    def _decode_tokens_inplace(self, x, stats, B, N, dev):
+    def _decode_tokens_inplace(self, x, st, B, N, dev):
         dec = self.decoder
-        run_blocks(self.dec_blocks, x, stats, B, N, self.ws)
+        run_blocks(self.dec_blocks, x, st, B, N, self.ws)
         g = dec.image_size // dec.patch_size
         img = torch.empty(B, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
         if dec.patch_size == 8 and dec.out_channels == 3:
             # decoder.norm folded into proj; un-patchify + clamp fused into the store
-            ops.gemm(x, self.w_proj, img, bias=self.b_proj, colsum=self.cs_proj, stats=stats,
-                     out_mode=PM_OUT_UNPATCH, patch=8, channels=3, grid=g)
+            ops.gemm(x, self.w_proj, img, bias=self.b_proj, colsum=self.cs_proj,
+                     out_mode=PM_OUT_UNPATCH, patch=8, channels=3, grid=g, **st.consume())
         else:
             raise RuntimeError("paintmind_b200 un-patchify epilogue is built for patch_size 8 / 3 channels")
         return img
@@ -313,10 +342,9 @@ class Stage1Engine:
         dec = self.decoder
         M, D = B * N, dec.dim
         x = self.ws.get("x", (M, D), torch.bfloat16, dev)
-        stats = self.ws.get("stats", (M, 2), torch.float32, dev)
-        ops.gemm(zs, self.w_post, x, bias=self.b_post, pos=self.dec_pos)          # post_quant + position embedding
-        ops.layernorm(x, stats=stats)
-        return self._decode_tokens_inplace(x, stats, B, N, dev)
+        st = _RowStats(self.ws, M, D, dev)
+        ops.gemm(zs, self.w_post, x, bias=self.b_post, pos=self.dec_pos, stats_out=st.produce())   # post_quant + pos-emb
+        return self._decode_tokens_inplace(x, st, B, N, dev)
 
     def decode_from_indice(self, indice):
         """ids [B, N] int64 -> image  (vqmodel.py:38-41, quantize.py:40-44)."""
@@ -342,10 +370,10 @@ class Stage1Engine:
         M = B * N
         dev = tokens.device
         x = self.ws.get("x", (M, D), torch.bfloat16, dev)
-        stats = self.ws.get("stats", (M, 2), torch.float32, dev)
+        st = _RowStats(self.ws, M, D, dev)
         x.copy_((tokens.detach().float() + self.dec_pos[None]).reshape(M, D))
-        ops.layernorm(x, stats=stats)
-        return self._decode_tokens_inplace(x, stats, B, N, dev)
+        ops.layernorm(x, stats=st.finished())
+        return self._decode_tokens_inplace(x, st, B, N, dev)
 
 
 class Stage2Engine:
@@ -415,16 +443,15 @@ class Stage2Engine:
         if N != self.pos.shape[0]:
             raise RuntimeError(f"expected {self.pos.shape[0]} tokens per sample, got {N}")
         x = self.ws.get("x", (M, D), torch.bfloat16, dev)
-        stats = self.ws.get("stats", (M, 2), torch.float32, dev)
-        ops.gemm(zs, self.w_tok, x, bias=self.b_tok, pos=self.pos)               # token_proj + position embedding
-        ops.layernorm(x, stats=stats)
+        st = _RowStats(self.ws, M, D, dev)
+        ops.gemm(zs, self.w_tok, x, bias=self.b_tok, pos=self.pos, stats_out=st.produce())   # token_proj + pos-emb
         kvs, L = None, 0
         if context is not None:
             kvs = self._context_kv(context)
             L = context.shape[1]
-        run_blocks(self.blocks, x, stats, B, N, self.ws, context_kv=kvs, ctx_len=L)
+        run_blocks(self.blocks, x, st, B, N, self.ws, context_kv=kvs, ctx_len=L)
         logits = torch.empty(M, tr.num_classes, device=dev, dtype=torch.float32)
-        ops.gemm(x, self.w_logits, logits, bias=self.b_logits, colsum=self.cs_logits, stats=stats, out_mode=PM_OUT_F32)
+        ops.gemm(x, self.w_logits, logits, bias=self.b_logits, colsum=self.cs_logits, out_mode=PM_OUT_F32, **st.consume())
         return logits.view(B, N, tr.num_classes)
 
     def forward(self, tokens, context=None):

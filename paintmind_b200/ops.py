@@ -50,8 +50,30 @@ def _require_cuda(*ts):
             raise RuntimeError("paintmind_b200 kernels need CUDA tensors (no CPU fallback)")
 
 
+def gemm_tile_n(n, out_mode=PM_OUT_BF16, swiglu=False):
+    """N-tile the library picks for bn = 0 (mirrors pm_gemm_bf16)."""
+    if swiglu:
+        return 256
+    if out_mode == PM_OUT_UNPATCH:
+        return 192 if n % 192 == 0 else 64
+    if n % 256 == 0:
+        return 256
+    if n % 128 == 0:
+        return 128
+    if n % 64 == 0 or out_mode == PM_OUT_BF16:
+        return 64
+    return 32
+
+
+def stats_parts(n, bn=None):
+    """Partial (sum, sum-of-squares) pairs per row that a GEMM with N = n writes to `stats_out`."""
+    bn = bn or gemm_tile_n(n)
+    return 2 * ((n + bn - 1) // bn)
+
+
 def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, out_mode=PM_OUT_BF16,
-         swiglu=False, bn=0, n=None, patch=0, channels=0, grid=0, max_ctas=0):
+         swiglu=False, bn=0, n=None, patch=0, channels=0, grid=0, max_ctas=0, stats_out=None, stats_raw=0,
+         ln_eps=1e-5, cta_group=0, debug=None):
     """out = epilogue(a[M,K] @ w[N,K]^T); see pm_gemm_bf16 in include/paintmind_b200.h."""
     _require_cuda(a, w, out)
     args = _lib.GemmArgs()
@@ -66,6 +88,9 @@ def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, o
     args.pos_rows = pos.shape[0] if pos is not None else 0
     args.out_mode, args.swiglu, args.bn = out_mode, int(bool(swiglu)), bn
     args.patch, args.channels, args.grid, args.max_ctas = patch, channels, grid, max_ctas
+    args.stats_raw, args.ln_eps, args.stats_out = int(stats_raw), float(ln_eps), _ptr(stats_out)
+    args.cta_group = int(cta_group)
+    args.debug = _ptr(debug)
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_gemm_bf16(C.byref(args), _stream()), "pm_gemm_bf16")
     _prof_end(t0, ("gemm", args.M, args.N, args.K, bool(swiglu), res is not None, stats is not None, out_mode))

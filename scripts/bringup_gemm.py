@@ -29,7 +29,7 @@ def ptr(t):
 
 
 def run_gemm(a, w, out, bias=None, colsum=None, stats=None, pos=None, res=None, out_mode=0, swiglu=0, bn=0,
-             patch=0, channels=0, grid=0, max_ctas=0, N=None):
+             patch=0, channels=0, grid=0, max_ctas=0, N=None, cta_group=1, stats_out=None, stats_raw=0):
     args = _lib.GemmArgs()
     args.a, args.w, args.out = ptr(a), ptr(w), ptr(out)
     args.bias, args.colsum, args.stats, args.pos, args.res = ptr(bias), ptr(colsum), ptr(stats), ptr(pos), ptr(res)
@@ -41,6 +41,7 @@ def run_gemm(a, w, out, bias=None, colsum=None, stats=None, pos=None, res=None, 
     args.pos_rows = pos.shape[0] if pos is not None else 0
     args.out_mode, args.swiglu, args.bn = out_mode, swiglu, bn
     args.patch, args.channels, args.grid, args.max_ctas = patch, channels, grid, max_ctas
+    args.cta_group, args.stats_out, args.stats_raw, args.ln_eps = cta_group, ptr(stats_out), stats_raw, 1e-5
     rc = lib.pm_gemm_bf16(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "pm_gemm_bf16")
 
@@ -163,6 +164,54 @@ def main():
     y = (a.float() @ w.float().t() + bias).reshape(B, G, G, P, P, Cc).permute(0, 5, 1, 3, 2, 4).reshape(B, Cc, G * P, G * P).clamp(-1, 1)
     all_ok &= report("unpatchify", img.reshape(-1, G * P), y.reshape(-1, G * P), 2e-3)
 
+    # 6b. CTA pairs (tcgen05.mma.cta_group::2, 256x256 tiles)
+    for (M, N, K, mc) in [(256, 256, 64, 0), (256, 256, 512, 0), (512, 512, 512, 1), (4096, 1536, 512, 0), (1000, 512, 1408, 3)]:
+        a, w = mk(M, N, K)
+        out = torch.full((M, N), float("nan"), device=dev)
+        run_gemm(a, w, out, out_mode=1, bn=256, cta_group=2, max_ctas=mc)
+        torch.cuda.synchronize()
+        all_ok &= report(f"PAIR f32 M{M} N{N} K{K} maxpairs{mc}", out, a.float() @ w.float().t(), 2e-3)
+        bias = torch.randn(N, device=dev)
+        res = torch.randn(M, N, device=dev).bfloat16()
+        x = res.clone()
+        P = 2 * ((N + 255) // 256)
+        st = torch.full((M, P, 2), float("nan"), device=dev)
+        run_gemm(a, w, x, bias=bias, res=x, out_mode=0, bn=256, cta_group=2, max_ctas=mc, stats_out=st)
+        st = st.sum(1)
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().t() + bias + res.float()
+        all_ok &= report(f"PAIR bf16+bias+res in place", x, ref, 1e-2)
+        all_ok &= report(f"   stats_out sum", st[:, 0], ref.sum(1), 2e-3)
+        all_ok &= report(f"   stats_out sumsq", st[:, 1], (ref ** 2).sum(1), 2e-3)
+    # raw stats consumed by an LN-folded GEMM (single CTA and pair)
+    for cg in (1, 2):
+        M, N, K = 2048, 1536, 512
+        x = (torch.randn(M, K, device=dev) * 2 + 0.5).bfloat16()
+        xf = x.float()
+        raw = torch.stack([xf[:, :200].sum(1), (xf[:, :200] ** 2).sum(1), xf[:, 200:].sum(1), (xf[:, 200:] ** 2).sum(1)], 1).contiguous()
+        gamma = torch.rand(K, device=dev) + 0.5; beta = torch.randn(K, device=dev) * 0.1
+        W = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev) * 0.1
+        Wf = (W * gamma).bfloat16(); colsum = Wf.float().sum(1); biasf = b + W @ beta
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        run_gemm(x, Wf, out, bias=biasf, colsum=colsum, stats=raw, stats_raw=2, out_mode=0, bn=256, cta_group=cg)
+        torch.cuda.synchronize()
+        all_ok &= report(f"LN-fold from raw sums cta_group={cg}", out, torch.nn.functional.layer_norm(xf, (K,), gamma, beta, 1e-5) @ W.t() + b, 2e-2)
+    # SwiGLU on pairs
+    M, K, hid = 1024, 512, 1408
+    a, _ = mk(M, 8, K)
+    Wg = (torch.randn(hid, K, device=dev) / K ** 0.5); Wv = (torch.randn(hid, K, device=dev) / K ** 0.5)
+    bg = torch.randn(hid, device=dev) * 0.1; bv = torch.randn(hid, device=dev) * 0.1
+    Wp = torch.empty(2 * hid, K, device=dev); bp = torch.empty(2 * hid, device=dev)
+    for t in range(hid // 128):
+        Wp[t * 256:t * 256 + 128] = Wg[t * 128:(t + 1) * 128]; Wp[t * 256 + 128:(t + 1) * 256] = Wv[t * 128:(t + 1) * 128]
+        bp[t * 256:t * 256 + 128] = bg[t * 128:(t + 1) * 128]; bp[t * 256 + 128:(t + 1) * 256] = bv[t * 128:(t + 1) * 128]
+    Wp = Wp.bfloat16()
+    out = torch.empty(M, hid, device=dev, dtype=torch.bfloat16)
+    run_gemm(a, Wp, out, bias=bp, out_mode=0, swiglu=1, cta_group=2)
+    torch.cuda.synchronize()
+    g = a.float() @ Wg.bfloat16().float().t() + bg; v = a.float() @ Wv.bfloat16().float().t() + bv
+    all_ok &= report("PAIR SwiGLU", out, torch.nn.functional.silu(g) * v, 2e-2)
+
     # 7. timing at the bench shapes (B=256 images -> M=262144)
     M = 262144
     for (name, N, K, bn, kw) in [("qkv", 1536, 512, 256, {}), ("out+res", 512, 512, 256, {"res": True}),
@@ -173,19 +222,20 @@ def main():
         out = torch.empty(M, nout, device=dev, dtype=torch.bfloat16)
         res = torch.randn(M, nout, device=dev).bfloat16() if kw.get("res") else None
         bias = torch.randn(N, device=dev)
-        for _ in range(3):
-            run_gemm(a, w, out, bias=bias, res=res, out_mode=0, swiglu=kw.get("swiglu", 0), bn=bn)
-        torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
         iters = 10
-        for _ in range(iters):
-            run_gemm(a, w, out, bias=bias, res=res, out_mode=0, swiglu=kw.get("swiglu", 0), bn=bn)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        flops = 2.0 * M * N * K
-        bytes_ = 2.0 * (M * K + N * K + M * nout * (2 if res is not None else 1))
-        log(f"[perf] {name}: M{M} N{N} K{K} bn{bn}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  {bytes_ / ms / 1e6:.0f} GB/s")
+        for cg in ((1, 2) if bn == 256 else (1,)):
+            for _ in range(3):
+                run_gemm(a, w, out, bias=bias, res=res, out_mode=0, swiglu=kw.get("swiglu", 0), bn=bn, cta_group=cg)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                run_gemm(a, w, out, bias=bias, res=res, out_mode=0, swiglu=kw.get("swiglu", 0), bn=bn, cta_group=cg)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            flops = 2.0 * M * N * K
+            bytes_ = 2.0 * (M * K + N * K + M * nout * (2 if res is not None else 1))
+            log(f"[perf] {name}: M{M} N{N} K{K} bn{bn} cta_group={cg}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  {bytes_ / ms / 1e6:.0f} GB/s")
         # cuBLAS reference time for context (plain matmul, no epilogue)
         wt = w.t().contiguous()
         for _ in range(2):
