@@ -44,9 +44,10 @@ int pm_gemm_bf16(const pm_gemm_args* a, void* stream) {
   p.max_ctas = a->max_ctas;
   p.stats_out = a->stats_out; p.stats_raw = a->stats_raw; p.ln_eps = a->ln_eps > 0.0f ? a->ln_eps : 1e-5f;
   if (p.stats_out != nullptr && (a->out_mode != PM_OUT_BF16 || a->swiglu)) return PM_ERR_INVALID;
-  // auto: CTA pairs pay off when the main loop is long (K >= 1024) or the epilogue is heavy (SwiGLU); measured on
-  // B200 at M = 262144: qkv/out (K = 512) 0.388/0.163 ms single vs 0.394/0.171 pair; w12/w3 0.650/0.357 vs 0.627/0.321
-  p.cta_pair = a->cta_group == 2 ? 1 : (a->cta_group == 1 ? 0 : ((a->swiglu || a->K >= 1024) ? 1 : 0));
+  if (p.stats_raw < 0 || p.stats_raw > 8 || (p.stats_raw & 1)) return PM_ERR_INVALID;   // partial pairs come in (tile, group) twos
+  // auto: CTA pairs (256 x 256 tiles, half the W traffic per SM) whenever the tile shape allows it.  Measured on B200 at
+  // M = 262144, single vs pair: qkv 0.389 / 0.352 ms, out 0.163 / 0.158, w12+SwiGLU 0.652 / 0.602, w3 0.357 / 0.319.
+  p.cta_pair = a->cta_group == 1 ? 0 : 1;
   p.debug = reinterpret_cast<long long*>(a->debug);
   if ((p.colsum == nullptr) != (p.stats == nullptr)) return PM_ERR_INVALID;
   int bn = a->bn;

@@ -336,8 +336,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Relaxed remote arrive: the only data it publishes are completed tcgen05.ld reads, which are ordered by
+// tcgen05.fence::before_thread_sync — a .release.cluster arrive would add a cluster-scope memory barrier
+// (ERRBAR/MEMBAR, ~20% of the epilogue's time when measured) for nothing.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of the pair; the transaction bytes are credited to the mbarrier at the
 // same offset in the EVEN (leader) CTA: clearing bit 24 of a shared::cta window address selects the peer.

@@ -242,6 +242,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     };
     if (OUT_MODE == OUT_BF16 && has_res && leader && group_chunks > 0) issue_res(0);
 
+    // per-row LayerNorm statistics, prefetched one tile ahead so their global-load latency is off the critical path
+    float4 spf[4];
+    auto prefetch_stats = [&](int tile_) {
+      const int r_ = tile_coord(tile_, n_tiles, BN, TILE_M, m_off).m0 + row_in_tile;
+      if (p.stats != nullptr && r_ < p.M) {
+        if (p.stats_raw > 0) {
+          const float4* sp = reinterpret_cast<const float4*>(p.stats + 2 * static_cast<size_t>(p.stats_raw) * r_);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (2 * i < p.stats_raw) spf[i] = sp[i];
+        } else {
+          const float2 t2 = *reinterpret_cast<const float2*>(p.stats + 2 * static_cast<size_t>(r_));
+          spf[0] = make_float4(t2.x, t2.y, 0.0f, 0.0f);
+        }
+      }
+    };
+    if (first_tile < total_tiles) prefetch_stats(first_tile);
+
     int as = 0;
     uint32_t aphase = 0;
     int gl = 0;   // chunks stored so far by this group (staging buffer = gl % NSTG_G)
@@ -258,27 +276,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         colvec[i] = (p.bias != nullptr && col < p.N) ? p.bias[col] : 0.0f;
         colvec[BN + i] = (p.colsum != nullptr && col < p.N) ? p.colsum[col] : 0.0f;
       }
+      // LayerNorm statistics of this row were prefetched one tile ahead (spf); turn them into (mean, rstd)
       float mu = 0.0f, rstd = 1.0f;
       if (p.stats != nullptr && row_ok) {
-        const float2 st = p.stats_raw > 0 ? make_float2(0.0f, 1.0f) : *reinterpret_cast<const float2*>(p.stats + 2 * static_cast<size_t>(row));
-        mu = st.x;
-        rstd = st.y;
         if (p.stats_raw > 0) {
           // p.stats_raw partial (sum, sum of squares) pairs per row, written by the epilogue of the GEMM that
           // produced A (one pair per N-tile and epilogue group); summed here in a fixed order -> deterministic
-          const float* sp = p.stats + 2 * static_cast<size_t>(p.stats_raw) * row;
           float s1 = 0.0f, s2 = 0.0f;
-          for (int i = 0; i < p.stats_raw; ++i) {
-            const float2 t = *reinterpret_cast<const float2*>(sp + 2 * i);
-            s1 += t.x;
-            s2 += t.y;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (2 * i < p.stats_raw) {
+              s1 += spf[i].x + spf[i].z;
+              s2 += spf[i].y + spf[i].w;
+            }
           }
           const float inv_k = 1.0f / static_cast<float>(p.K);
           mu = s1 * inv_k;
           const float var = fmaxf(s2 * inv_k - mu * mu, 0.0f);
           rstd = rsqrtf(var + p.ln_eps);
+        } else {
+          mu = spf[0].x;
+          rstd = spf[0].y;
         }
       }
+      if (tile + tile_stride < total_tiles) prefetch_stats(tile + tile_stride);
       float row_s1 = 0.0f, row_s2 = 0.0f;   // statistics of this thread's output columns (for the next LayerNorm)
       const float nrmu = -rstd * mu;        // LN fold: rstd * (acc - mu * colsum) + bias == acc * rstd + (nrmu * colsum + bias)
       const float* pos_row = nullptr;
