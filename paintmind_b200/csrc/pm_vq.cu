@@ -12,10 +12,10 @@
 //     B row (K = 64)  = [ e_hi | e_lo ]                   (ONE slab, reused for both A slabs)
 // which reproduces the fp32 dot product to ~1e-7 (bf16 x bf16 products are exact in fp32).
 //
-// vq_main_kernel: work item = (256-row tile, codebook split).  320 threads:
+// vq_main_kernel: work item = (256-row tile, codebook split).  352 threads:
 //   warp 0 lane 0 : TMA producer — streams the packed codebook [n_e, 64] bf16 (1 MB for 8192
 //                   codes) through a 6-stage smem ring of 128-code tiles
-//   warp 1 lane 0 : MMA issuer   — 2 row halves x 8 k-steps of 128x128x16 per code tile into
+//   warps 1, 10   : MMA issuers  — one thread per 128-row half: 8 k-steps of 128x128x16 per code tile into
 //                   double-buffered TMEM accumulators (4 x 128 columns)
 //   warps 2..9    : one thread per latent row: normalise z, write the split A tile into swizzled
 //                   smem, then drain the accumulators with a running (max, first index) pair.
@@ -32,7 +32,7 @@ constexpr int VQ_BN = 128;               // codes per tile
 constexpr int VQ_BSTAGES = 6;
 constexpr int VQ_A_SLAB = 128 * 128;     // 16 KB: 128 rows x 64 bf16
 constexpr int VQ_B_BYTES = VQ_BN * 128;  // 16 KB
-constexpr int VQ_THREADS = 320;
+constexpr int VQ_THREADS = 352;            // TMA warp, MMA warp (row half 0), 8 drain warps, MMA warp (row half 1)
 constexpr int VQ_SMEM_BYTES = 1024 + 4 * VQ_A_SLAB + VQ_BSTAGES * VQ_B_BYTES + 512;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -136,9 +136,9 @@ vq_main_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + VQ_BSTAGES * VQ_B_BYTES);
   uint64_t* b_full = bars;                             // [VQ_BSTAGES]
   uint64_t* b_empty = bars + VQ_BSTAGES;               // [VQ_BSTAGES]
-  uint64_t* t_full = bars + 2 * VQ_BSTAGES;            // [2]
-  uint64_t* t_empty = t_full + 2;                      // [2]
-  uint64_t* a_full = t_empty + 2;                      // [1]  A tile written (256 arrivals)
+  uint64_t* t_full = bars + 2 * VQ_BSTAGES;            // [2 stages][2 row halves]
+  uint64_t* t_empty = t_full + 4;                      // [2 stages][2 row halves]
+  uint64_t* a_full = t_empty + 4;                      // [1]  A tile written (8 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -153,11 +153,11 @@ vq_main_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < VQ_BSTAGES; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], 2);       // one commit per MMA issuer (row half)
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 8);       // one arrival per drain warp
+      mbar_init(&t_empty[i], 4);       // one arrival per drain warp of that row half
     }
     mbar_init(a_full, 8);
     fence_mbar_init();
@@ -186,9 +186,12 @@ vq_main_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
+    // two MMA issuer threads, one per 128-row half: the 128x128x16 MMAs are short (64 tensor cycles), a single
+    // issuing thread cannot keep the pipe fed
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, VQ_BN, 0, 0);
+      const int rh = (warp == 1) ? 0 : 1;
       int st = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -199,28 +202,25 @@ vq_main_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
         item_ph ^= 1;
         tc_fence_after();
         for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(&t_empty[as], aph ^ 1);
+          mbar_wait(&t_empty[as * 2 + rh], aph ^ 1);
           mbar_wait(&b_full[st], ph);
           tc_fence_after();
           const uint64_t db = umma_desc_sw128(smem_u32(smB + st * VQ_B_BYTES));
+          const uint32_t tacc = tmem_base + (as * 2 + rh) * VQ_BN;
 #pragma unroll
-          for (int rh = 0; rh < 2; ++rh) {
-            const uint32_t tacc = tmem_base + (as * 2 + rh) * VQ_BN;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              // A k-step k: slab k/4 (z_hi|z_hi , z_lo|z_lo), 32 B step inside; B: [e_hi|e_lo] k%4
-              const uint64_t da = umma_desc_sw128(smem_u32(smA + (rh * 2 + (k >> 2)) * VQ_A_SLAB)) + 2 * (k & 3);
-              umma_ss(tacc, da, db + 2 * (k & 3), idesc, k != 0 ? 1u : 0u);
-            }
+          for (int k = 0; k < 8; ++k) {
+            // A k-step k: slab k/4 (z_hi|z_hi , z_lo|z_lo), 32 B step inside; B: [e_hi|e_lo] k%4
+            const uint64_t da = umma_desc_sw128(smem_u32(smA + (rh * 2 + (k >> 2)) * VQ_A_SLAB)) + 2 * (k & 3);
+            umma_ss(tacc, da, db + 2 * (k & 3), idesc, k != 0 ? 1u : 0u);
           }
           umma_commit(&b_empty[st]);
-          umma_commit(&t_full[as]);
+          umma_commit(&t_full[as * 2 + rh]);
           if (++st == VQ_BSTAGES) { st = 0; ph ^= 1; }
           if (++as == 2) { as = 0; aph ^= 1; }
         }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 10) {
     const int q = warp & 3;
     const int rh = (warp - 2) >> 2;                    // row half 0/1
     const int r_in_half = q * 32 + lane;               // 0..127
@@ -271,7 +271,7 @@ vq_main_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
       float best = -INFINITY;
       int bidx = code0;
       for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(&t_full[as], aph);
+        mbar_wait(&t_full[as * 2 + rh], aph);
         tc_fence_after();
         const uint32_t tacc = tmem_base + lane_off + (as * 2 + rh) * VQ_BN;
         const int cbase = code0 + t * VQ_BN;
@@ -285,26 +285,31 @@ vq_main_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
             // last TMEM read of this accumulator stage
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[as]);
+            if (lane == 0) mbar_arrive(&t_empty[as * 2 + rh]);
           }
-          if (!tail) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float v = __uint_as_float(r[i]);
-              const bool gt = v > best;
-              best = gt ? v : best;
-              bidx = gt ? (cbase + cc * 32 + i) : bidx;
-            }
-          } else {
+          if (tail) {
+            // codes beyond this split / the codebook (TMA zero-filled rows) must never win
             const int lim = min(code0 + codes_per_split, p.n_e);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int code = cbase + cc * 32 + i;
-              const float v = __uint_as_float(r[i]);
-              const bool gt = (v > best) && (code < lim);
-              best = gt ? v : best;
-              bidx = gt ? code : bidx;
-            }
+            for (int i = 0; i < 32; ++i)
+              if (cbase + cc * 32 + i >= lim) r[i] = 0xff800000u;   // -inf
+          }
+          // chunk maximum with a short dependency chain (3-input max tree); the running (max, first index) pair is
+          // only touched when this chunk beats it — rare after the first few tiles — so the 8192-long compare/select
+          // chain of a naive scan never forms
+          float m8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            m8[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                          fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+          const float cm = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+          if (cm > best) {          // strict: an equal value in a later chunk never replaces an earlier index (torch.argmin rule)
+            best = cm;
+            int first = 31;
+#pragma unroll
+            for (int i = 30; i >= 0; --i)
+              if (__uint_as_float(r[i]) == cm) first = i;
+            bidx = cbase + cc * 32 + first;
           }
         }
         if (++as == 2) { as = 0; aph ^= 1; }
@@ -416,10 +421,12 @@ int pm_vq_launch(const VqParams& p_in, cudaStream_t stream) {
   if (p.z == nullptr || p.en == nullptr || p.packed == nullptr || p.M <= 0 || p.n_e <= 0) return PM_ERR_INVALID;
   if (p.e_dim != VQ_D || (p.ldz % 4) != 0) return PM_ERR_INVALID;
   if (p.splits <= 0) {
-    // enough work items to fill the machine ~4x over, while keeping >= 8 code tiles per split
+    // split the codebook over several CTAs per row tile only when the row tiles alone cannot fill the machine
+    // (the merge costs a second kernel and every split re-normalises its rows): measured at M = 65536,
+    // 256 row tiles: 117 us unsplit vs 138 us with 4 splits
     const int row_tiles = (p.M + VQ_BM - 1) / VQ_BM;
     int s = 1;
-    while (row_tiles * s < 4 * pm_num_sms() && (p.n_e / (s * 2)) >= 8 * VQ_BN && (p.n_e % (s * 2 * VQ_BN)) == 0 && s < 8) s *= 2;
+    while (row_tiles * s < pm_num_sms() && (p.n_e / (s * 2)) >= 8 * VQ_BN && (p.n_e % (s * 2 * VQ_BN)) == 0 && s < 8) s *= 2;
     p.splits = s;
   }
   if (p.n_e % p.splits != 0) return PM_ERR_INVALID;
