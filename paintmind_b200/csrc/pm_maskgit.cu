@@ -151,6 +151,197 @@ maskgit_sample_kernel(const MaskgitParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory staged variant (V % 128 == 0, row <= 64 KB): each warp pulls its whole logit row into shared
+// memory with ONE 1-D bulk TMA copy (cp.async.bulk + mbarrier), then makes two cheap passes over it:
+//   pass 1: row max and, per lane, the two largest values (branch-free max/min network) -> tau = k-th largest of
+//           the 64 lane leaders, a lower bound of the row's k-th largest value
+//   pass 2: sum of exp(x - max) and the few candidates x >= tau (warp-aggregated append), from which the exact
+//           top-k (ties -> lower index) is selected
+// Streaming insertion sort (the kernel above) diverges on almost every element; this one is HBM-bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int MG_CAND = 128;     // candidate capacity per row (expected: k .. ~2k entries)
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+maskgit_sample_smem_kernel(const MaskgitParams p) {
+  extern __shared__ __align__(128) uint8_t mg_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_bytes = p.V * 4;
+  float* buf = reinterpret_cast<float*>(mg_smem + static_cast<size_t>(warp) * row_bytes);
+  uint8_t* tail = mg_smem + static_cast<size_t>(WARPS) * row_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail) + warp;
+  float* cand_v = reinterpret_cast<float*>(tail + 64) + warp * MG_CAND;
+  int* cand_i = reinterpret_cast<int*>(tail + 64 + WARPS * MG_CAND * 4) + warp * MG_CAND;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const int k = p.topk;
+  const int nvec = p.V >> 2;
+  uint32_t phase = 0;
+  const int row_stride = gridDim.x * WARPS;
+  for (int row = blockIdx.x * WARPS + warp; row < p.M; row += row_stride) {
+    // ---- one bulk copy of the row: global -> shared ----
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, static_cast<uint32_t>(row_bytes));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(buf)), "l"(reinterpret_cast<uint64_t>(p.logits + static_cast<size_t>(row) * p.ld)),
+                   "r"(static_cast<uint32_t>(row_bytes)), "r"(smem_u32(bar))
+                   : "memory");
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    const float4* b4 = reinterpret_cast<const float4*>(buf);
+    // ---- pass 1: lane-local two largest values (4 independent max/min chains for ILP: few warps per SM) ----
+    float t0 = -INFINITY, t1 = -INFINITY;
+    {
+      float u0[4], u1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { u0[u] = -INFINITY; u1[u] = -INFINITY; }
+      for (int c = lane; c < nvec; c += 128) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = (c + 32 * u < nvec) ? b4[c + 32 * u] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            u1[u] = fmaxf(u1[u], fminf(u0[u], e[t]));
+            u0[u] = fmaxf(u0[u], e[t]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        t1 = fmaxf(t1, fminf(t0, u0[u]));
+        t0 = fmaxf(t0, u0[u]);
+        t1 = fmaxf(t1, fminf(t0, u1[u]));       // u1[u] <= u0[u] <= t0: only t1 can change
+      }
+    }
+    float mw = t0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    // tau = k-th largest of the 64 lane leaders (k <= 32): k rounds of warp max with removal
+    float a0 = t0, a1 = t1, tau = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      float bv = a0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bv = fmaxf(bv, __shfl_xor_sync(0xffffffffu, bv, o));
+      tau = bv;
+      const unsigned who = __ballot_sync(0xffffffffu, a0 == bv);
+      if (lane == __ffs(who) - 1) { a0 = a1; a1 = -INFINITY; }      // pop from exactly one lane
+    }
+    // ---- pass 2: softmax denominator (4 independent partial sums) and candidates >= tau ----
+    float ssum = 0.0f;
+    int ncand = 0;                                                    // warp-uniform
+    {
+      float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const float nm = -mw * 1.4426950408889634f;
+      for (int c = lane; c < nvec; c += 128) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = (c + 32 * u < nvec) ? b4[c + 32 * u] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float ex;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(e[t], 1.4426950408889634f, nm)));
+            ps[u] += ex;
+            any |= (e[t] >= tau);
+          }
+        }
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const bool hit = e[t] >= tau;
+              const unsigned m = __ballot_sync(0xffffffffu, hit);
+              if (hit) {
+                const int pos = ncand + __popc(m & ((1u << lane) - 1u));
+                if (pos < MG_CAND) { cand_v[pos] = e[t]; cand_i[pos] = (c + 32 * u) * 4 + t; }
+              }
+              ncand += __popc(m);
+            }
+          }
+        }
+      }
+      ssum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    __syncwarp();
+    ncand = min(ncand, MG_CAND);
+    // ---- exact top-k among the candidates (value desc, index asc); lane r keeps winner r ----
+    float cv[MG_CAND / 32];
+    int ci[MG_CAND / 32];
+#pragma unroll
+    for (int u = 0; u < MG_CAND / 32; ++u) {
+      const int j = u * 32 + lane;
+      cv[u] = j < ncand ? cand_v[j] : -INFINITY;
+      ci[u] = j < ncand ? cand_i[j] : 0x7fffffff;
+    }
+    float my_v = -INFINITY;
+    int my_i = 0x7fffffff;
+    for (int r = 0; r < k; ++r) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < MG_CAND / 32; ++u)
+        if (cv[u] > bv || (cv[u] == bv && ci[u] < bi)) { bv = cv[u]; bi = ci[u]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+#pragma unroll
+      for (int u = 0; u < MG_CAND / 32; ++u)
+        if (ci[u] == bi) { cv[u] = -INFINITY; ci[u] = 0x7fffffff; }   // remove the winner (indices are unique)
+      if (lane == r) { my_v = bv; my_i = bi; }
+    }
+    // ---- gumbel-perturbed arg-max over the k survivors (generate.py:45-46) ----
+    float score = -INFINITY;
+    if (lane < k && my_i != 0x7fffffff) {
+      float u;
+      if (p.noise != nullptr) u = p.noise[static_cast<size_t>(row) * p.ld_noise + my_i];
+      else u = philox_uniform(p.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(my_i), static_cast<uint32_t>(p.offset));
+      const float inner = -logf(fmaxf(u, 1e-20f));
+      const float g = -logf(fmaxf(inner, 1e-20f));
+      score = my_v / fmaxf(p.temperature, 1e-10f) + g;
+    }
+    float bs = score;
+    int bi = (lane < k) ? my_i : 0x7fffffff;
+    float bl = my_v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; bl = ol; }
+    }
+    if (lane == 0) {
+      const long long pred = static_cast<long long>(bi);
+      const float prob = __expf(bl - mw) / ssum;                 // softmax(logits)[pred], unfiltered, T = 1
+      if (p.pred_ids != nullptr) p.pred_ids[row] = pred;
+      bool is_mask = true;
+      if (p.ids != nullptr) {
+        is_mask = (p.ids[row] == p.mask_id);
+        if (is_mask) p.ids[row] = pred;                          // fill the mask, keep the unmasked
+      }
+      if (p.scores != nullptr) p.scores[row] = is_mask ? (1.0f - prob) : -1e5f;
+    }
+    __syncwarp();      // all lanes done with buf / candidates before the next bulk copy overwrites them
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // re-mask: per image, the k highest scores get mask_id (ties: lower token index first).
 // rank_i = #{j : s_j > s_i  or (s_j == s_i and j < i)};  token i is re-masked iff rank_i < k.
 // ---------------------------------------------------------------------------------------------
@@ -176,6 +367,26 @@ maskgit_remask_kernel(const float* __restrict__ scores, long long* __restrict__ 
 int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
   if (p.logits == nullptr || p.M <= 0 || p.V <= 0 || (p.V & 3) != 0 || (p.ld & 3) != 0) return PM_ERR_INVALID;
   if (p.topk < 1 || p.topk > 32 || p.topk > p.V) return PM_ERR_INVALID;
+  const int row_bytes = p.V * 4;
+  if ((p.V % 128) == 0 && row_bytes <= 65536 && (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {
+    // shared-memory staged kernel: as many row buffers per SM as fit (6 x 32 KB for V = 8192)
+    constexpr int W = 6;
+    const int smem = W * row_bytes + 64 + W * MG_CAND * 8;
+    if (smem <= 232448 - 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(maskgit_sample_smem_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        attr_set = true;
+      }
+      const int per_sm = (232448 - 1024) / smem;                      // co-resident blocks when rows are short
+      int blocks = pm_num_sms() * (per_sm > 4 ? 4 : per_sm);
+      const int need = (p.M + W - 1) / W;
+      if (blocks > need) blocks = need;
+      maskgit_sample_smem_kernel<W><<<blocks, W * 32, smem, stream>>>(p);
+      return static_cast<int>(cudaGetLastError());
+    }
+  }
   const int threads = 256;
   const int blocks = (p.M + 7) / 8;
   if (p.topk <= 8) maskgit_sample_kernel<8><<<blocks, threads, 0, stream>>>(p);
