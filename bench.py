@@ -10,8 +10,9 @@ torch.distributed.run (one rank per GPU); work is batch-sharded (weak scaling: 2
 step) with a single NCCL all-reduce of the codebook-usage histogram + loss scalars at the end of the
 timed region.  Rank 0 prints ONE JSON line.
 
-`--impl reference` times the reference's CPU algorithm for the same path (the numpy oracle port of
-the pure-Python/torch reference, all host threads) on a bounded sample of the same workload.
+`--impl reference` times the reference's CPU algorithm for the same path (the torch-CPU oracle port of
+the pure-Python/torch reference: same ATen operators, fp32, all host threads) on a bounded sample of the
+same workload (4 images per step, the reference's own CPU-runnable case, BASELINE configs[0]).
 """
 from __future__ import annotations
 
@@ -45,25 +46,33 @@ def _peaks():
 # CPU arm: the oracle port of the reference algorithm (test infrastructure, used here ONLY as the
 # thing being timed for the cpu_baseline / reference arm — never on the product path)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_images_per_s(sample_batch: int, repeats: int = 1):
-    import numpy as np
+CPU_SAMPLE = 4      # images per CPU pass = the reference's own CPU-runnable case (BASELINE configs[0]: batch 4, fp32)
+
+
+def cpu_reference_images_per_s(sample_batch: int = CPU_SAMPLE, repeats: int = 1, warm: bool = True):
+    """Times encode+decode of `sample_batch` images with the torch-CPU oracle port (the same ATen CPU
+    operators the pure-Python reference dispatches to, all host threads, fp32, no autograd)."""
     import torch
-    from oracle import paintmind_oracle as O
+    from oracle import paintmind_oracle_torch as OT
     from paintmind_b200.config import ver2cfg
     from paintmind_b200.utils import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     cfg = ver2cfg["vit-s-vqgan"]
-    sd = {k: v.numpy() for k, v in synthetic.make_vqgan_state_dict(cfg, seed=0).items()}
-    x = synthetic.make_images(sample_batch, 256, seed=1000).numpy()
-    O.vqmodel_encode(x[:1, :, :, :], sd, cfg)          # warm-up (BLAS thread pools, page-in)
+    sd = synthetic.make_vqgan_state_dict(cfg, seed=0)
+    x = synthetic.make_images(sample_batch, 256, seed=1000)
     times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        z_q, loss, idx = O.vqmodel_encode(x, sd, cfg)
-        rec = O.vqmodel_decode(z_q, sd, cfg)
-        times.append(time.perf_counter() - t0)
-    assert np.isfinite(rec).all()
+    with torch.no_grad():
+        if warm:
+            OT.vqmodel_encode(x[:1], sd, cfg)               # warm-up (thread pools, page-in)
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            z_q, loss, idx = OT.vqmodel_encode(x, sd, cfg)
+            rec = OT.vqmodel_decode(z_q, sd, cfg)
+            times.append(time.perf_counter() - t0)
+    assert bool(torch.isfinite(rec).all())
     t = statistics.median(times)
-    return sample_batch / t, t
+    return sample_batch / t, sum(times)
 
 
 def run_reference(args):
@@ -71,23 +80,24 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    sample = 2
     vals = []
-    if args.warmup > 0:
-        cpu_reference_images_per_s(sample)              # one warm-up pass (BLAS pools, page-in)
+    for _ in range(args.warmup):
+        cpu_reference_images_per_s(CPU_SAMPLE)              # untimed warm-up passes
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
-        v, _ = cpu_reference_images_per_s(sample)
+        v, _ = cpu_reference_images_per_s(CPU_SAMPLE, warm=False)
         vals.append(v)
     wall = time.perf_counter() - t_all0
     value = statistics.median(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * CPU_SAMPLE / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": sample, "note": "bounded sample of the batch-256 workload"},
+        "config": {"workload": WORKLOAD, "batch_per_step": CPU_SAMPLE,
+                   "note": "bounded sample of the batch-256 workload: each step is one encode+decode pass over 4 images"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} images per step x {args.steps} steps (numpy fp32 oracle port of the reference, multithreaded BLAS)"},
+                         "sample": f"{CPU_SAMPLE} images per step x {args.steps} steps (torch-CPU fp32 oracle port of the "
+                                   f"reference: same ATen operators, {cores} threads)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
@@ -330,9 +340,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, secs = cpu_reference_images_per_s(2)
+        v, secs = cpu_reference_images_per_s(CPU_SAMPLE, repeats=5)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"2 images, one encode+decode pass of the numpy fp32 oracle port ({secs:.1f} s)"}
+               "sample": f"{CPU_SAMPLE} images x 5 encode+decode passes (median) of the torch-CPU fp32 oracle port, "
+                         f"all host threads ({secs:.1f} s of CPU work)"}
 
     if world > 1:
         dist.barrier()

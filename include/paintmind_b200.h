@@ -34,6 +34,8 @@ extern "C" {
 #define PM_OUT_BF16 0    /* bf16 row-major [M, N] (or [M, N/2] with swiglu) via TMA store      */
 #define PM_OUT_F32 1     /* fp32 row-major [M, N]                                              */
 #define PM_OUT_UNPATCH 2 /* fp32 NCHW image, clamp(-1,1): layers.py:150 + vqmodel.py:30        */
+#define PM_OUT_UNPATCH_U8 3 /* uint8 NHWC pixels: the same + `restore` (reconstruct.py:11-16):
+                               u = uint8(255 * ((clamp(v,-1,1) + 1) * 0.5)), patch 8, 3 channels  */
 
 /* Library / device introspection. */
 int pm_version(void);                 /* ABI version of this header (1)                        */
@@ -149,9 +151,13 @@ int pm_split_rows32(const float* src, int64_t ld, int32_t M, void* out_split, vo
  *   pm_layernorm : nn.LayerNorm over bf16 rows (layers.py:49,51,89,128; eps 1e-5).
  *                  y == NULL: only stats[row] = (mean, rstd) (feeds the LN-folded GEMM epilogue);
  *                  y != NULL: y = LN(x) * gamma + beta (bf16) and, if stats != NULL, the stats of y.
- * ------------------------------------------------------------------------------------------- */
+ *   pm_patchify8_u8 : the same im2col fed from decoded pixels, uint8 NHWC [B, H, W, 3] (8-byte aligned), with the
+ *                  reference's ingest transform fused (utils/transform.py:17-18: ToTensor u/255, Normalize
+ *                  (t-0.5)/0.5, evaluated in fp32 exactly as torchvision does) — SURVEY.md §8f row 3.
+ */
 /* pm_cast_f32_bf16 : fp32 -> bf16 (n % 8 == 0); the text context entering cross-attention k/v (transformer.py:84-86). */
 int pm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int pm_patchify8_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t W, void* stream);
 int pm_patchify8(const float* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 int pm_layernorm(const void* x, int64_t ldx, int32_t M, int32_t D, float eps, const float* gamma,
                  const float* beta, void* y, int64_t ldy, float* stats, void* stream);

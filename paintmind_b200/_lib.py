@@ -11,7 +11,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpaintmind_b200.so"
 _lib = None
 
-PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH = 0, 1, 2
+PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8 = 0, 1, 2, 3
 
 
 class GemmArgs(C.Structure):
@@ -98,6 +98,7 @@ EXPORTS = {
     "pm_vq_gather": [_p, _i32, _i32, _i32, _p, _i32, _p, _p, _p],
     "pm_split_rows32": [_p, _i64, _i32, _p, _p],
     "pm_patchify8": [_p, _p, _i32, _i32, _i32, _i32, _p],
+    "pm_patchify8_u8": [_p, _p, _i32, _i32, _i32, _p],
     "pm_layernorm": [_p, _i64, _i32, _i32, _f, _p, _p, _p, _i64, _p, _p],
     "pm_cast_f32_bf16": [_p, _p, _i64, _p],
     "pm_maskgit_sample": [C.POINTER(MaskgitSampleArgs), _p],

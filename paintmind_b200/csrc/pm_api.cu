@@ -53,13 +53,13 @@ int pm_gemm_bf16(const pm_gemm_args* a, void* stream) {
   int bn = a->bn;
   if (bn == 0) {
     if (a->swiglu) bn = 256;
-    else if (a->out_mode == PM_OUT_UNPATCH) bn = (p.N % 192 == 0) ? 192 : 64;
+    else if (a->out_mode == PM_OUT_UNPATCH || a->out_mode == PM_OUT_UNPATCH_U8) bn = (p.N % 192 == 0) ? 192 : 64;
     else if (p.N % 256 == 0) bn = 256;
     else if (p.N % 128 == 0) bn = 128;
     else if (p.N % 64 == 0 || a->out_mode == PM_OUT_BF16) bn = 64;
     else bn = 32;
   }
-  if (a->out_mode == PM_OUT_UNPATCH && (p.patch <= 0 || p.channels <= 0 || p.grid <= 0 ||
+  if ((a->out_mode == PM_OUT_UNPATCH || a->out_mode == PM_OUT_UNPATCH_U8) && (p.patch <= 0 || p.channels <= 0 || p.grid <= 0 ||
                                         p.N != p.patch * p.patch * p.channels))
     return PM_ERR_INVALID;
   return pm_gemm_launch(p, bn, a->out_mode, a->swiglu, static_cast<cudaStream_t>(stream));
@@ -108,6 +108,10 @@ int pm_split_rows32(const float* src, int64_t ld, int32_t M, void* out_split, vo
 
 int pm_patchify8(const float* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
   return pm_patchify_launch(img, out, B, C, H, W, 8, static_cast<cudaStream_t>(stream));
+}
+
+int pm_patchify8_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t W, void* stream) {
+  return pm_patchify_u8_launch(img, out, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
 int pm_layernorm(const void* x, int64_t ldx, int32_t M, int32_t D, float eps, const float* gamma,

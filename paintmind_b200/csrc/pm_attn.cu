@@ -24,6 +24,7 @@
 #include "pm_common.cuh"
 #include "pm_kernels.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace pm {
@@ -79,29 +80,52 @@ __device__ __forceinline__ AttnItem attn_item(int w, int n_qb, int H) {
   return it;
 }
 
-template <int EMU>
+// A never-taken, compiler-opaque branch: ends the basic block so that ptxas schedules the exponentials of one
+// sub-block (MUFU + FMA-pipe mix) before the next one instead of hoisting every polynomial chain to the front and
+// leaving a MUFU-only tail (measured: the two softmax warps of an SM sub-partition then fight for the 4-lane MUFU
+// while the FMA pipe idles, and vice versa).
+__device__ __forceinline__ void sched_fence(uint32_t tok) {
+  uint32_t v;
+  asm volatile("mov.b32 %0, %1;" : "=r"(v) : "r"(tok));
+  if (v == 0xffffffffu) __trap();
+}
+
+// EMU   : of every 4 pairs of scores, this many take the FMA-pipe exp2
+// SPLIT : sub-blocks of the exponential phase separated by scheduling fences (1 = none, 4 = per 32 keys, 8 = per 16)
+// CHAIN : > 0: groups of CHAIN score pairs are chained by a value-neutral dependency (see the exponential loop)
+// PING  : 2 = the exponential phases of the two softmax warps that share an SM sub-partition (warp q of Q tile 0 and
+//         warp q of Q tile 1) are made mutually exclusive with a pair of named barriers (ping-pong): measured, the two
+//         run in lock-step otherwise (the MMA warps hand S_0 and S_1 out back to back), so both sit in their MUFU-bound
+//         phase at the same time (MUFU saturated) and both in their load / max / store phases at the same time (MUFU
+//         idle).  1 = a one-time half-step delay of tile 1 instead.  0 = neither.
+// DEFER : where the wait for the previous P_t V sits: -1 = before the exponentials, c = 0..3 = after the
+//         exponentials of 32-key chunk c (P chunks are stored from there on; 3 = whole row kept in registers)
+template <int EMU, int SPLIT, int DEFER, int CHAIN, int PING>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
             const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smQ = smem;                                                   // [AT_Q_STAGES][2][16 KB]
-  uint8_t* smK = smQ + 2 * AT_Q_STAGES * AT_TILE_BYTES;                  // [AT_KV_STAGES][16 KB]
-  uint8_t* smV = smK + AT_KV_STAGES * AT_TILE_BYTES;                     // [AT_KV_STAGES][16 KB]
-  uint8_t* smO = smV + AT_KV_STAGES * AT_TILE_BYTES;                     // [2][16 KB] output staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smO + 2 * AT_TILE_BYTES);
-  uint64_t* q_full = bars;                                   // [2]
-  uint64_t* q_empty = q_full + AT_Q_STAGES;                  // [2]
-  uint64_t* k_full = q_empty + AT_Q_STAGES;                  // [3]
-  uint64_t* k_empty = k_full + AT_KV_STAGES;                 // [3]
-  uint64_t* v_full = k_empty + AT_KV_STAGES;                 // [3]
-  uint64_t* v_empty = v_full + AT_KV_STAGES;                 // [3]
-  uint64_t* s_full = v_empty + AT_KV_STAGES;                 // [2]  MMA -> softmax: S_t complete
-  uint64_t* s_free = s_full + 2;                             // [2]  softmax -> MMA: S_t is in registers
-  uint64_t* p_full = s_free + 2;                             // [2]  softmax -> MMA: P_t written (and O_t rescaled)
-  uint64_t* pv_done = p_full + 2;                            // [2]  MMA -> softmax: O_t += P_t V complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  // everything is addressed by 32-bit shared::cta addresses (no generic-window rebuilds in the hot loops)
+  const uint32_t raw_a = smem_u32(smem_raw);
+  const uint32_t sQ = (raw_a + 1023u) & ~1023u;                          // [AT_Q_STAGES][2][16 KB]
+  const uint32_t sK = sQ + 2 * AT_Q_STAGES * AT_TILE_BYTES;              // [AT_KV_STAGES][16 KB]
+  const uint32_t sV = sK + AT_KV_STAGES * AT_TILE_BYTES;                 // [AT_KV_STAGES][16 KB]
+  const uint32_t sO = sV + AT_KV_STAGES * AT_TILE_BYTES;                 // [2][16 KB] output staging
+  const uint32_t bars = sO + 2 * AT_TILE_BYTES;
+  const uint32_t q_full = bars;                                   // [2]
+  const uint32_t q_empty = q_full + 8 * AT_Q_STAGES;              // [2]
+  const uint32_t k_full = q_empty + 8 * AT_Q_STAGES;              // [3]
+  const uint32_t k_empty = k_full + 8 * AT_KV_STAGES;             // [3]
+  const uint32_t v_full = k_empty + 8 * AT_KV_STAGES;             // [3]
+  const uint32_t v_empty = v_full + 8 * AT_KV_STAGES;             // [3]
+  const uint32_t s_full = v_empty + 8 * AT_KV_STAGES;             // [2]  MMA -> softmax: S_t complete
+  const uint32_t s_free = s_full + 16;                            // [2]  softmax -> MMA: S_t is in registers
+  const uint32_t p_full = s_free + 16;                            // [2]  softmax -> MMA: P_t written (and O_t rescaled)
+  const uint32_t pv_done = p_full + 16;                           // [2]  MMA -> softmax: O_t += P_t V complete
+  const uint32_t tmem_slot_a = pv_done + 16;
+  uint8_t* const smO = smem_raw + (sO - raw_a);                   // generic view of the staging tiles
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot_a - raw_a));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,21 +143,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
+    auto init = [](uint32_t bar, uint32_t count) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    };
     for (int i = 0; i < AT_Q_STAGES; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
+      init(q_full + 8 * i, 1);
+      init(q_empty + 8 * i, 1);
     }
     for (int i = 0; i < AT_KV_STAGES; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      init(k_full + 8 * i, 1);
+      init(k_empty + 8 * i, 1);
+      init(v_full + 8 * i, 1);
+      init(v_empty + 8 * i, 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 4);      // one arrival per softmax warp of the group
-      mbar_init(&p_full[t], 4);
-      mbar_init(&pv_done[t], 1);
+      init(s_full + 8 * t, 1);
+      init(s_free + 8 * t, 4);      // one arrival per softmax warp of the group
+      init(p_full + 8 * t, 4);
+      init(pv_done + 8 * t, 1);
     }
     fence_mbar_init();
   }
@@ -155,19 +182,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         for (int i = 0; i < my_items; ++i) {
           const AttnItem it = attn_item(blockIdx.x + i * gridDim.x, n_qb, p.H);
           const int qs = i % AT_Q_STAGES;
-          mbar_wait(&q_empty[qs], ((i / AT_Q_STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&q_full[qs], 2 * AT_TILE_BYTES);
-          tma_load_3d(smQ + (2 * qs) * AT_TILE_BYTES, &tmQ, &q_full[qs], it.h * AT_D, it.qb * 2 * AT_BM, it.b);
-          tma_load_3d(smQ + (2 * qs + 1) * AT_TILE_BYTES, &tmQ, &q_full[qs], it.h * AT_D, it.qb * 2 * AT_BM + AT_BM, it.b);
+          mbar_wait_a(q_empty + 8 * qs, ((i / AT_Q_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx_a(q_full + 8 * qs, 2 * AT_TILE_BYTES);
+          tma_load_3d_a(sQ + (2 * qs) * AT_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * AT_D, it.qb * 2 * AT_BM, it.b);
+          tma_load_3d_a(sQ + (2 * qs + 1) * AT_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * AT_D, it.qb * 2 * AT_BM + AT_BM, it.b);
           for (int j = 0; j < n_kv; ++j, ++g) {
             const int st = g % AT_KV_STAGES;
             const uint32_t ph = ((g / AT_KV_STAGES) & 1) ^ 1;
-            mbar_wait(&k_empty[st], ph);
-            mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
-            tma_load_3d(smK + st * AT_TILE_BYTES, &tmK, &k_full[st], it.h * AT_D, j * AT_BN, it.b);
-            mbar_wait(&v_empty[st], ph);
-            mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
-            tma_load_3d(smV + st * AT_TILE_BYTES, &tmV, &v_full[st], it.h * AT_D, j * AT_BN, it.b);
+            mbar_wait_a(k_empty + 8 * st, ph);
+            mbar_arrive_expect_tx_a(k_full + 8 * st, AT_TILE_BYTES);
+            tma_load_3d_a(sK + st * AT_TILE_BYTES, &tmK, k_full + 8 * st, it.h * AT_D, j * AT_BN, it.b);
+            mbar_wait_a(v_empty + 8 * st, ph);
+            mbar_arrive_expect_tx_a(v_full + 8 * st, AT_TILE_BYTES);
+            tma_load_3d_a(sV + st * AT_TILE_BYTES, &tmV, v_full + 8 * st, it.h * AT_D, j * AT_BN, it.b);
           }
         }
       }
@@ -178,25 +205,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       if (lane == 0 && total_steps > 0) {
         constexpr uint32_t idesc_qk = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);   // Q, K both K-major
         const uint32_t tS[2] = {tmem_base, tmem_base + 128};
-        const uint32_t q_base = smem_u32(smQ), k_base = smem_u32(smK);
         for (int g = 0; g < total_steps; ++g) {
           const int i = g / n_kv, j = g - i * n_kv;
           const int qs = i % AT_Q_STAGES, ks = g % AT_KV_STAGES;
-          if (j == 0) mbar_wait(&q_full[qs], (i / AT_Q_STAGES) & 1);
-          mbar_wait(&k_full[ks], (g / AT_KV_STAGES) & 1);
-          const uint64_t dk = umma_desc_sw128(k_base + ks * AT_TILE_BYTES);
+          if (j == 0) mbar_wait_a(q_full + 8 * qs, (i / AT_Q_STAGES) & 1);
+          mbar_wait_a(k_full + 8 * ks, (g / AT_KV_STAGES) & 1);
+          const uint64_t dk = umma_desc_sw128(sK + ks * AT_TILE_BYTES);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             // S_t of the previous step must be in the softmax threads' registers before it is overwritten
-            if (g > 0) mbar_wait(&s_free[t], (g - 1) & 1);
+            if (g > 0) mbar_wait_a(s_free + 8 * t, (g - 1) & 1);
             tc_fence_after();
-            const uint64_t dq = umma_desc_sw128(q_base + (2 * qs + t) * AT_TILE_BYTES);
+            const uint64_t dq = umma_desc_sw128(sQ + (2 * qs + t) * AT_TILE_BYTES);
 #pragma unroll
             for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS[t], dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-            umma_commit(&s_full[t]);
+            umma_commit_a(s_full + 8 * t);
           }
-          umma_commit(&k_empty[ks]);                            // both tiles have used K(g)
-          if (j == n_kv - 1) umma_commit(&q_empty[qs]);         // last use of this item's Q
+          umma_commit_a(k_empty + 8 * ks);                            // both tiles have used K(g)
+          if (j == n_kv - 1) umma_commit_a(q_empty + 8 * qs);         // last use of this item's Q
         }
       }
     } else if (warp == 10) {
@@ -205,24 +231,23 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         constexpr uint32_t idesc_pv = umma_idesc_bf16(AT_BM, AT_D, 0, 1);    // P K-major (TMEM), V MN-major
         const uint32_t tP[2] = {tmem_base + 256, tmem_base + 320};
         const uint32_t tO[2] = {tmem_base + 384, tmem_base + 448};
-        const uint32_t v_base = smem_u32(smV);
         for (int g = 0; g < total_steps; ++g) {
           const int j = g % n_kv;
           const int vs = g % AT_KV_STAGES;
-          mbar_wait(&v_full[vs], (g / AT_KV_STAGES) & 1);
-          const uint64_t dv = umma_desc_sw128(v_base + vs * AT_TILE_BYTES);
+          mbar_wait_a(v_full + 8 * vs, (g / AT_KV_STAGES) & 1);
+          const uint64_t dv = umma_desc_sw128(sV + vs * AT_TILE_BYTES);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            mbar_wait(&p_full[t], g & 1);
+            mbar_wait_a(p_full + 8 * t, g & 1);
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < AT_BN / 16; ++kk) {
               // A: 16 keys = 8 TMEM columns of packed bf16;  B: 16 key rows x 128 B = 2048 B
               umma_ts(tO[t], tP[t] + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0 ? 1u : 0u);
             }
-            umma_commit(&pv_done[t]);
+            umma_commit_a(pv_done + 8 * t);
           }
-          umma_commit(&v_empty[vs]);
+          umma_commit_a(v_empty + 8 * vs);
         }
       }
     }
@@ -236,19 +261,28 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const uint32_t tS = tmem_base + t * 128 + lane_off;
     const uint32_t tP = tmem_base + 256 + t * 64 + lane_off;
     const uint32_t tO = tmem_base + 384 + t * 64 + lane_off;
+    const uint32_t b_s_full = s_full + 8 * t, b_s_free = s_free + 8 * t;
+    const uint32_t b_p_full = p_full + 8 * t, b_pv_done = pv_done + 8 * t;
     const float c = p.scale_log2;                  // softmax scale * log2(e)
     uint8_t* stg_base = smO + t * AT_TILE_BYTES;
     uint8_t* stg = stg_base + row_in_tile * 128;
     int g = 0;                                     // flattened step counter (barrier phases)
+    if (PING == 2 && t == 1 && total_steps > 0) asm volatile("bar.arrive %0, 64;" ::"r"(3 + 2 * q) : "memory");   // tile 0 goes first
+    if (PING == 1 && t == 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < 900) {
+      }
+    }
 
     for (int i = 0; i < my_items; ++i) {
       const AttnItem it = attn_item(blockIdx.x + i * gridDim.x, n_qb, p.H);
       float m_used = -INFINITY;                    // running max (scaled, log2 domain) the accumulators refer to
-      float2 l2 = make_float2(0.0f, 0.0f);         // running sum of exp2(s*c - m_used), two partial lanes
+      float2 la = make_float2(0.0f, 0.0f);         // running sum of exp2(s*c - m_used): four partial sums
+      float2 lb = make_float2(0.0f, 0.0f);         //   (two packed accumulators = two short dependency chains)
 
       for (int j = 0; j < n_kv; ++j, ++g) {
         const int valid = p.Nk - j * AT_BN;        // >= 128 for full tiles
-        mbar_wait(&s_full[t], g & 1);
+        mbar_wait_a(b_s_full, g & 1);
         tc_fence_after();
         // ---- whole score row into registers ----
         uint32_t s[4][32];
@@ -260,7 +294,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         // the score row is in registers: S_t may be overwritten by the next Q K^T
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[t]);
+        if (lane == 0) mbar_arrive_a(b_s_free);
         if (valid < AT_BN) {                       // ragged last key tile (e.g. 77 text tokens): mask the tail
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
@@ -279,17 +313,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         // lazy rescale: keep the stale max while it is within 2^8 of the true one (exact algebra,
         // bounded magnitude); decided per warp to keep the TMEM traffic warp-uniform
         const bool need = (m_new - m_used) > 8.0f;
-        if (j > 0) {
-          // O_t and P_t are still being read by P_t V of the previous step until this fires (normally long ago)
-          mbar_wait(&pv_done[t], (g - 1) & 1);
+        if (DEFER < 0 && j > 0) {
+          // O_t and P_t are still being read by P_t V of the previous step until this fires
+          mbar_wait_a(b_pv_done, (g - 1) & 1);
           tc_fence_after();
         }
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
           if (need) m_used = m_new;
-          l2.x *= alpha;
-          l2.y *= alpha;
+          la.x *= alpha;
+          la.y *= alpha;
+          lb.x *= alpha;
+          lb.y *= alpha;
           if (j > 0) {
+            if (DEFER >= 0) {
+              // O_t is still being accumulated by P_t V of the previous step until this fires
+              mbar_wait_a(b_pv_done, (g - 1) & 1);
+              tc_fence_after();
+            }
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               uint32_t r[32];
@@ -302,31 +343,53 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           }
         }
         // ---- P = exp2(s*c - m_used) -> packed bf16 into the P_t columns ----
+        if (PING == 2) asm volatile("bar.sync %0, 64;" ::"r"(3 + 2 * q + t) : "memory");      // my turn on the MUFU
         const float2 cc2 = make_float2(c, c);
-        const float2 mm2 = make_float2(-m_used, -m_used);
+        float2 mm2 = make_float2(-m_used, -m_used);
+        uint32_t pk[4][16];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
+            if (SPLIT == 8 && e == 16) sched_fence(static_cast<uint32_t>(g));
             const float2 x = make_float2(__uint_as_float(s[ch][e]), __uint_as_float(s[ch][e + 1]));
             const float2 a = __ffma2_rn(x, cc2, mm2);
             const float2 ex = (((e >> 1) & 3) < EMU) ? exp2_poly2(a) : make_float2(ex2_approx(a.x), ex2_approx(a.y));
-            l2 = __fadd2_rn(l2, ex);
-            pk[e >> 1] = pack_bf16x2(ex.x, ex.y);
+            if (CHAIN > 0 && ((e >> 1) % (CHAIN > 0 ? CHAIN : 1)) == CHAIN - 1 && !(ch == 3 && e + 2 * CHAIN >= 32)) {
+              // Ordering dependency (value-neutral: ex is finite, ex * 0 + mm == mm): the next group's scores are scaled
+              // with an offset that "depends" on a MUFU result of this group, so ptxas cannot hoist every polynomial
+              // chain of the row to the front and leave a MUFU-only tail; each group keeps its own MUFU / FMA mix.
+              mm2 = __ffma2_rn(ex, make_float2(0.0f, 0.0f), mm2);
+            }
+            if ((e >> 1) & 1) lb = __fadd2_rn(lb, ex);
+            else la = __fadd2_rn(la, ex);
+            pk[ch][e >> 1] = pack_bf16x2(ex.x, ex.y);
           }
-          tmem_st_x16(tP + ch * 16, pk);
+          if (DEFER >= 0 && ch == DEFER) {
+            if (j > 0) {
+              // the P_t columns are read by P_t V of the previous step until this fires — this late it practically
+              // always has (the wait used to sit in front of the exponentials and cost ~11 % of the softmax time)
+              mbar_wait_a(b_pv_done, (g - 1) & 1);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int c2 = 0; c2 < ch; ++c2) tmem_st_x16(tP + c2 * 16, pk[c2]);
+          }
+          if (DEFER < 0 || ch >= DEFER) tmem_st_x16(tP + ch * 16, pk[ch]);
+          if (SPLIT >= 4 && ch < 3) sched_fence(static_cast<uint32_t>(g));
         }
+        if (PING == 2 && !(t == 1 && g == total_steps - 1))
+          asm volatile("bar.arrive %0, 64;" ::"r"(3 + 2 * q + (t ^ 1)) : "memory");           // the partner warp's turn
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive_a(b_p_full);
       }
 
       // ---- item epilogue: O / l -> bf16 -> swizzled smem staging -> TMA store ----
-      mbar_wait(&pv_done[t], (g - 1) & 1);
+      mbar_wait_a(b_pv_done, (g - 1) & 1);
       tc_fence_after();
-      const float inv_l = 1.0f / (l2.x + l2.y);
+      const float inv_l = 1.0f / ((la.x + la.y) + (lb.x + lb.y));
       uint32_t r0[32], r1[32];
       tmem_ld_x32(tO, r0);
       tmem_ld_x32(tO + 32, r1);
@@ -358,7 +421,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         asm volatile(
             "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
             ::"l"(reinterpret_cast<uint64_t>(&tmO)),
-            "r"(smem_u32(stg_base)), "r"(it.h * AT_D), "r"(it.qb * 2 * AT_BM + t * AT_BM), "r"(it.b)
+            "r"(sO + t * AT_TILE_BYTES), "r"(it.h * AT_D), "r"(it.qb * 2 * AT_BM + t * AT_BM), "r"(it.b)
             : "memory");
         tma_store_commit();
       }
@@ -375,6 +438,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 }
 
+using AttnKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+
+struct AttnVariant {
+  int emu, split, defer, chain, ping;
+  AttnKernelFn fn;
+};
+#define PM_ATTN_V(E, S, D, C, P) {E, S, D, C, P, attn_kernel<E, S, D, C, P>}
+// The first entry is the default.  PM_ATTN_VARIANT="emu,split,defer,chain,ping" picks another one (tuning aid; every
+// variant computes the same function).
+static const AttnVariant kAttnVariants[] = {
+    // measured on B200 (B = 256, H = 8, N = 1024; scripts/attn_variants.py, profiles/r01_attn_variants.txt):
+    PM_ATTN_V(1, 1, 3, 8, 0),    // 0.656 ms  default: deferred P_t V wait, groups of 8 pairs chained
+    PM_ATTN_V(1, 1, -1, 0, 0),   // 0.684-0.690 ms  the previous kernel (wait in front of the exponentials)
+    PM_ATTN_V(1, 1, 3, 0, 0),    // 0.661-0.668 ms  deferred wait only
+    PM_ATTN_V(1, 1, 3, 8, 2),    // 0.661 ms  + ping-pong barriers between the two warps of a sub-partition (no gain)
+    PM_ATTN_V(2, 1, 3, 8, 0),    //           half of the exponentials on the FMA pipe
+    PM_ATTN_V(0, 1, 3, 0, 0),    // 0.736 ms  every exponential on the MUFU
+};
+#undef PM_ATTN_V
+
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream) {
   if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.o == nullptr) return PM_ERR_INVALID;
   if (p.B <= 0 || p.H <= 0 || p.Nq <= 0 || p.Nk <= 0 || p.head_dim != AT_D) return PM_ERR_INVALID;
@@ -385,24 +468,25 @@ int pm_attn_launch(const AttnParams& p, cudaStream_t stream) {
   if ((rc = pm_make_tmap_3d(&tmK, p.k, 2, p.B, p.Nk, inner, p.ldk, p.bsk, AT_BN, AT_D)) != PM_OK) return rc;
   if ((rc = pm_make_tmap_3d(&tmV, p.v, 2, p.B, p.Nk, inner, p.ldv, p.bsv, AT_BN, AT_D)) != PM_OK) return rc;
   if ((rc = pm_make_tmap_3d(&tmO, p.o, 2, p.B, p.Nq, inner, p.ldo, p.bso, AT_BM, AT_D)) != PM_OK) return rc;
-  // fraction of exponentials on the FMA pipe: 0, 1/4 (default) or 1/2; PM_ATTN_EMU overrides (tuning aid)
-  static int emu = -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    const char* env = getenv("PM_ATTN_EMU");
-    emu = env != nullptr ? atoi(env) : 1;
-    if (emu < 0 || emu > 2) emu = 1;
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+  static AttnKernelFn fn = nullptr;
+  if (fn == nullptr) {
+    const AttnVariant* v = &kAttnVariants[0];
+    const char* env = getenv("PM_ATTN_VARIANT");
+    if (env != nullptr) {
+      int e = -9, s = -9, d = -9, ch = -9, pg = -9;
+      if (sscanf(env, "%d,%d,%d,%d,%d", &e, &s, &d, &ch, &pg) != 5) return PM_ERR_INVALID;
+      v = nullptr;
+      for (const AttnVariant& c : kAttnVariants)
+        if (c.emu == e && c.split == s && c.defer == d && c.chain == ch && c.ping == pg) v = &c;
+      if (v == nullptr) return PM_ERR_INVALID;
+    }
+    const cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    fn = v->fn;
   }
   const long long items = static_cast<long long>((p.Nq + 2 * AT_BM - 1) / (2 * AT_BM)) * p.H * p.B;
   const int grid = items < pm_num_sms() ? static_cast<int>(items) : pm_num_sms();
-  if (emu == 0) attn_kernel<0><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
-  else if (emu == 2) attn_kernel<2><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
-  else attn_kernel<1><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  fn<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return static_cast<int>(cudaGetLastError());
 }
 

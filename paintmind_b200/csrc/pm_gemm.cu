@@ -423,6 +423,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (tc.n0 + oc + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               }
             }
+          } else if (OUT_MODE == OUT_UNPATCH_U8) {
+            // column = (p1 * 8 + p2) * 3 + ch -> uint8 NHWC pixel out[b, h*8 + p1, w*8 + p2, ch] = the reference's
+            // `restore` (reconstruct.py:11-16) of the clamped reconstruction, operation by operation in fp32:
+            // x = clamp(v, -1, 1); t = (x + 1) * 0.5; u = uint8(trunc(255 * t)).  Four consecutive columns are four
+            // consecutive bytes of one pixel row of the patch (24 % 4 == 0), so they leave as one 32-bit store.
+            if (row_ok) {
+              const int G = p.grid;
+              const int tok = row % (G * G), bimg = row / (G * G);
+              const int th = tok / G, tw = tok % G;
+              const int S = G * 8;
+              uint8_t* img = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(bimg) * S + th * 8) * S * 3 + tw * 24;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int col = tc.n0 + oc + j;
+                if (col < p.N) {
+                  uint32_t w = 0;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float x = fminf(fmaxf(v[j + e], -1.0f), 1.0f);
+                    const float t = __fmul_rn(__fadd_rn(x, 1.0f), 0.5f);
+                    w |= static_cast<uint32_t>(__float2int_rz(__fmul_rn(255.0f, t))) << (8 * e);
+                  }
+                  const int p1 = col / 24, r = col - p1 * 24;
+                  *reinterpret_cast<uint32_t*>(img + static_cast<size_t>(p1) * S * 3 + r) = w;
+                }
+              }
+            }
           } else {  // OUT_UNPATCH: column = (p1 * P + p2) * C + ch  ->  out[b, ch, h*P + p1, w*P + p2]
             if (row_ok) {
               const int P = p.patch, C = p.channels, G = p.grid;   // G tokens per image side
@@ -581,6 +608,14 @@ int pm_gemm_launch(const GemmParams& p, int bn, int out_mode, int swiglu, cudaSt
     switch (bn) {
       case 64:  return launch_gemm<64, OUT_UNPATCH, false, false>(p, stream);
       case 192: return launch_gemm<192, OUT_UNPATCH, false, false>(p, stream);
+      default:  return PM_ERR_INVALID;
+    }
+  }
+  if (out_mode == OUT_UNPATCH_U8) {
+    if (p.patch != 8 || p.channels != 3 || p.N != 192 || (reinterpret_cast<uintptr_t>(p.out) & 3) != 0) return PM_ERR_INVALID;
+    switch (bn) {
+      case 64:  return launch_gemm<64, OUT_UNPATCH_U8, false, false>(p, stream);
+      case 192: return launch_gemm<192, OUT_UNPATCH_U8, false, false>(p, stream);
       default:  return PM_ERR_INVALID;
     }
   }

@@ -5,7 +5,7 @@
 
 namespace pm {
 
-enum : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_UNPATCH = 2 };
+enum : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_UNPATCH = 2, OUT_UNPATCH_U8 = 3 };
 
 struct GemmParams {
   const void* a;
@@ -81,6 +81,7 @@ int pm_vq_launch(const VqParams& p, cudaStream_t stream);
 int pm_vq_gather_launch(const long long* idx, int M, int n_rows, const float* table, int normalize,
                         float* out, void* out_split, cudaStream_t stream);
 int pm_split_rows32_launch(const float* src, int64_t ld, int M, void* out_split, cudaStream_t stream);
+int pm_patchify_u8_launch(const uint8_t* img, void* out, int B, int H, int W, cudaStream_t stream);
 int pm_patchify_launch(const float* img, void* out, int B, int C, int H, int W, int P, cudaStream_t stream);
 int pm_layernorm_launch(const void* x, int64_t ldx, int M, int D, float eps, const float* gamma,
                         const float* beta, void* y, int64_t ldy, float* stats, cudaStream_t stream);

@@ -33,6 +33,46 @@ __global__ void patchify8_kernel(const float* __restrict__ img, __nv_bfloat16* _
 }
 
 // ----------------------------------------------------------------------------------------------
+// Same im2col, fed straight from decoded pixels: uint8 NHWC [B, H, W, 3] (PIL / numpy layout).  Fuses the
+// reference's ingest transform (utils/transform.py:17-18: T.ToTensor() = u / 255, T.Normalize(0.5, 0.5) =
+// (t - 0.5) / 0.5, both in fp32 — reproduced here operation by operation, so the result is bit-identical to
+// patchify8 of the fp32 tensor the reference would have built) into the patch extraction: 3 B/px are read instead
+// of 12 B/px and the fp32 NCHW image (4x the size of the pixels) never exists.
+// thread = (b, y, tw): reads 8 pixels x 3 channels = 24 contiguous bytes, writes three 16-byte rows.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float norm_u8(uint32_t u) {
+  const float t = __fdiv_rn(static_cast<float>(u), 255.0f);          // ToTensor
+  return __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);                        // Normalize(mean 0.5, std 0.5)
+}
+
+__global__ void patchify8_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  const int gw = W >> 3, gh = H >> 3;
+  const long long total = static_cast<long long>(B) * H * gw;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int tw = static_cast<int>(t % gw);
+  const long long r = t / gw;
+  const int y = static_cast<int>(r % H);
+  const int b = static_cast<int>(r / H);
+  const uint2* src = reinterpret_cast<const uint2*>(img + ((static_cast<size_t>(b) * H + y) * W + tw * 8) * 3);
+  const uint2 w0 = src[0], w1 = src[1], w2 = src[2];
+  const uint32_t wd[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+  float v[3][8];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i % 3][i / 3] = norm_u8((wd[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+  const int th = y >> 3, kh = y & 7;
+  const size_t row = (static_cast<size_t>(b) * gh + th) * gw + tw;
+  __nv_bfloat16* dst = out + row * 192 + kh * 8;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(v[c][0], v[c][1]); o.y = pack_bf16x2(v[c][2], v[c][3]);
+    o.z = pack_bf16x2(v[c][4], v[c][5]); o.w = pack_bf16x2(v[c][6], v[c][7]);
+    *reinterpret_cast<uint4*>(dst + c * 64) = o;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // LayerNorm over rows of a bf16 [M, D] matrix (D % 8 == 0, D <= 2048), eps inside the sqrt,
 // biased variance — nn.LayerNorm semantics (stage1/layers.py:49,51,89,128).
 //   MODE 0: stats only  -> stats[row] = (mean, rstd)   (consumed by the LN-folded GEMM epilogue)
@@ -159,6 +199,16 @@ int pm_patchify_launch(const float* img, void* out, int B, int C, int H, int W, 
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   patchify8_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, C, H, W);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int pm_patchify_u8_launch(const uint8_t* img, void* out, int B, int H, int W, cudaStream_t stream) {
+  if (img == nullptr || out == nullptr || (H % 8) != 0 || (W % 8) != 0 || B <= 0) return PM_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(img) & 7) != 0) return PM_ERR_INVALID;
+  const long long total = static_cast<long long>(B) * H * (W / 8);
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  patchify8_u8_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, H, W);
   return static_cast<int>(cudaGetLastError());
 }
 

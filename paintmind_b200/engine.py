@@ -22,7 +22,7 @@ import weakref
 import torch
 
 from . import ops
-from .ops import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH
+from .ops import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8
 
 LN_EPS = 1e-5
 
@@ -257,18 +257,26 @@ class Stage1Engine:
 
     # -- encoder -------------------------------------------------------------------------------
     def run_encoder(self, img):
-        """img fp32 NCHW in [-1, 1] -> tokens bf16 [B, N, D]  (Encoder.forward, layers.py:106-112)."""
+        """img fp32 NCHW in [-1, 1] -> tokens bf16 [B, N, D]  (Encoder.forward, layers.py:106-112).
+        A uint8 [B, H, W, 3] tensor (decoded pixels) is also accepted: the reference's ingest transform
+        (utils/transform.py:17-18, ToTensor + Normalize(0.5, 0.5)) is then fused into the patch extraction."""
         self._ensure_packed()
         enc = self.encoder
         if not img.is_cuda:
             raise RuntimeError("paintmind_b200: input must be a CUDA tensor (no CPU fallback)")
         img = img.detach()
-        if img.dtype != torch.float32:
-            img = img.float()
-        img = img.contiguous()
-        B, C, H, W = img.shape
+        pixels = img.dtype == torch.uint8
+        if pixels:
+            img = img.contiguous()
+            B, H, W, C = img.shape
+        else:
+            if img.dtype != torch.float32:
+                img = img.float()
+            img = img.contiguous()
+            B, C, H, W = img.shape
         if H != enc.image_size or W != enc.image_size or C != enc.in_channels:
-            raise RuntimeError(f"expected input [B,{enc.in_channels},{enc.image_size},{enc.image_size}], got {tuple(img.shape)}")
+            raise RuntimeError(f"expected input [B,{enc.in_channels},{enc.image_size},{enc.image_size}] "
+                               f"(or uint8 [B,{enc.image_size},{enc.image_size},{enc.in_channels}]), got {tuple(img.shape)}")
         g = H // 8
         N, D = g * g, enc.dim
         M = B * N
@@ -278,7 +286,10 @@ class Stage1Engine:
         x0 = ws.get("x0", (M, D), torch.bfloat16, dev)
         x = ws.get("x", (M, D), torch.bfloat16, dev)
         st = _RowStats(ws, M, D, dev)
-        ops.patchify8(img, patches)
+        if pixels:
+            ops.patchify8_u8(img, patches)
+        else:
+            ops.patchify8(img, patches)
         ops.gemm(patches, self.w_pe, x0, pos=self.enc_pos)                        # conv-as-GEMM + position embedding
         ops.layernorm(x0, gamma=self.pre_g, beta=self.pre_b, y=x, stats=st.finished())   # norm_pre (+ stats of its output)
         run_blocks(self.enc_blocks, x, st, B, N, ws)
@@ -306,21 +317,26 @@ class Stage1Engine:
         return z.view(B, N, -1)
 
     # -- decoder -------------------------------------------------------------------------------
-    def _decode_tokens_inplace(self, x, st, B, N, dev):
+    def _decode_tokens_inplace(self, x, st, B, N, dev, pixels=False):
         dec = self.decoder
         run_blocks(self.dec_blocks, x, st, B, N, self.ws)
         g = dec.image_size // dec.patch_size
-        img = torch.empty(B, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
-        if dec.patch_size == 8 and dec.out_channels == 3:
-            # decoder.norm folded into proj; un-patchify + clamp fused into the store
-            ops.gemm(x, self.w_proj, img, bias=self.b_proj, colsum=self.cs_proj,
-                     out_mode=PM_OUT_UNPATCH, patch=8, channels=3, grid=g, **st.consume())
-        else:
+        if dec.patch_size != 8 or dec.out_channels != 3:
             raise RuntimeError("paintmind_b200 un-patchify epilogue is built for patch_size 8 / 3 channels")
+        # decoder.norm folded into proj; un-patchify + clamp (+ `restore` to uint8 pixels) fused into the store
+        if pixels:
+            img = torch.empty(B, dec.image_size, dec.image_size, 3, device=dev, dtype=torch.uint8)
+            mode = PM_OUT_UNPATCH_U8
+        else:
+            img = torch.empty(B, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
+            mode = PM_OUT_UNPATCH
+        ops.gemm(x, self.w_proj, img, bias=self.b_proj, colsum=self.cs_proj,
+                 out_mode=mode, patch=8, channels=3, grid=g, **st.consume())
         return img
 
-    def decode(self, z):
-        """z [B, N, 32] -> image [B, 3, H, W] in [-1, 1]  (VQModel.decode, vqmodel.py:27-30)."""
+    def decode(self, z, pixels=False):
+        """z [B, N, 32] -> image [B, 3, H, W] in [-1, 1]  (VQModel.decode, vqmodel.py:27-30);
+        pixels=True -> uint8 [B, H, W, 3] = restore(decode(z)) (reconstruct.py:11-16)."""
         self._ensure_packed()
         dec = self.decoder
         if not z.is_cuda:
@@ -336,17 +352,17 @@ class Stage1Engine:
             z2d = z2d.contiguous()
         zs = self.ws.get("zs", (M, 2 * E), torch.bfloat16, dev)
         ops.split_rows32(z2d, zs)
-        return self._decode_split(zs, B, N, dev)
+        return self._decode_split(zs, B, N, dev, pixels)
 
-    def _decode_split(self, zs, B, N, dev):
+    def _decode_split(self, zs, B, N, dev, pixels=False):
         dec = self.decoder
         M, D = B * N, dec.dim
         x = self.ws.get("x", (M, D), torch.bfloat16, dev)
         st = _RowStats(self.ws, M, D, dev)
         ops.gemm(zs, self.w_post, x, bias=self.b_post, pos=self.dec_pos, stats_out=st.produce())   # post_quant + pos-emb
-        return self._decode_tokens_inplace(x, st, B, N, dev)
+        return self._decode_tokens_inplace(x, st, B, N, dev, pixels)
 
-    def decode_from_indice(self, indice):
+    def decode_from_indice(self, indice, pixels=False):
         """ids [B, N] int64 -> image  (vqmodel.py:38-41, quantize.py:40-44)."""
         self._ensure_packed()
         m = self.model
@@ -358,7 +374,7 @@ class Stage1Engine:
         E = m.quantize.embedding.weight.detach().float().contiguous()
         zs = self.ws.get("zs", (M, 2 * m.quantize.e_dim), torch.bfloat16, dev)
         ops.vq_gather(indice.reshape(-1).to(torch.int64).contiguous(), E, True, None, zs)
-        return self._decode_split(zs, B, N, dev)
+        return self._decode_split(zs, B, N, dev, pixels)
 
     def run_decoder_tokens(self, tokens):
         """Decoder.forward on [B, N, D] tokens (layers.py:145-152) -> un-clamped?  NOTE: the fused

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH  # noqa: F401
+from ._lib import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8  # noqa: F401
 
 
 # Optional per-launch timing (bench.py): when PROFILE is a dict, every op records CUDA events on the
@@ -54,7 +54,7 @@ def gemm_tile_n(n, out_mode=PM_OUT_BF16, swiglu=False):
     """N-tile the library picks for bn = 0 (mirrors pm_gemm_bf16)."""
     if swiglu:
         return 256
-    if out_mode == PM_OUT_UNPATCH:
+    if out_mode in (PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8):
         return 192 if n % 192 == 0 else 64
     if n % 256 == 0:
         return 256
@@ -81,7 +81,7 @@ def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, o
     args.bias, args.colsum, args.stats = _ptr(bias), _ptr(colsum), _ptr(stats)
     args.pos, args.res = _ptr(pos), _ptr(res)
     args.lda, args.ldw = a.stride(0), w.stride(0)
-    args.ld_out = out.stride(0) if out_mode != PM_OUT_UNPATCH else 0
+    args.ld_out = out.stride(0) if out_mode not in (PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8) else 0
     args.ld_pos = pos.stride(0) if pos is not None else 0
     args.ld_res = res.stride(0) if res is not None else 0
     args.M, args.N, args.K = a.shape[0], (n if n is not None else w.shape[0]), a.shape[1]
@@ -165,6 +165,18 @@ def patchify8(img, out):
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_patchify8(_ptr(img), _ptr(out), B, Cc, H, W, _stream()), "pm_patchify8")
     _prof_end(t0, ("patchify8", B))
+    return out
+
+
+def patchify8_u8(img_u8, out):
+    """uint8 NHWC [B, H, W, 3] pixels -> normalised bf16 patch rows (ToTensor + Normalize(0.5, 0.5) fused)."""
+    _require_cuda(img_u8, out)
+    B, H, W, Cc = img_u8.shape
+    if Cc != 3 or img_u8.dtype != torch.uint8 or not img_u8.is_contiguous():
+        raise RuntimeError("patchify8_u8 expects a contiguous uint8 [B, H, W, 3] tensor")
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_patchify8_u8(_ptr(img_u8), _ptr(out), B, H, W, _stream()), "pm_patchify8_u8")
+    _prof_end(t0, ("patchify8_u8", B))
     return out
 
 

@@ -51,6 +51,27 @@ class VQModel(nn.Module):
     def from_pretrained(self, path):
         return self.load_state_dict(torch.load(path))
 
+    # -- pixels in / pixels out (the steps either side of the path) ----------
+    @torch.no_grad()
+    def encode_pixels(self, img_u8):
+        """encode() of decoded pixels: uint8 [B, H, W, 3] (PIL / numpy layout).  Equals
+        encode(Normalize(0.5, 0.5)(ToTensor(img))) of the reference's ingest transform
+        (utils/transform.py:17-18, reconstruct.py:31-37) — the transform is fused into the patch
+        extraction kernel, so the fp32 NCHW image (4x the pixel bytes) never exists."""
+        if img_u8.dtype != torch.uint8:
+            raise TypeError("encode_pixels expects uint8 [B, H, W, 3]")
+        return self.engine().encode(img_u8)
+
+    @torch.no_grad()
+    def decode_pixels(self, x):
+        """restore(decode(x)) of reconstruct.py:11-16,37-39 as uint8 [B, H, W, 3]: (x+1)*0.5, HWC,
+        uint8(255*x) — fused into the un-patchify epilogue of the last projection."""
+        return self.engine().decode(x, pixels=True)
+
+    @torch.no_grad()
+    def decode_pixels_from_indice(self, indice):
+        return self.engine().decode_from_indice(indice, pixels=True)
+
     # -- engine ------------------------------------------------------------------------------
     def engine(self):
         if self._engine is None:

@@ -32,7 +32,7 @@ def _worker(rank, world, port, total, q):
     hist = torch.bincount(idx.reshape(-1), minlength=64)
     sums = torch.tensor([float(sse.sum()), float(idx.numel() * 32)], dtype=torch.float64)
     pmdist.allreduce_usage(hist, sums)
-    q.put((rank, lo, hi, hist, sums))
+    q.put((rank, lo, hi, hist.tolist(), sums.tolist()))      # plain lists: no shared-memory handles outlive the worker
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,6 +62,7 @@ def test_allreduce_usage_world2_equals_single_process():
     want_hist = torch.bincount(idx.reshape(-1), minlength=64)
     want_sums = torch.tensor([float(sse.sum()), float(idx.numel() * 32)], dtype=torch.float64)
     for rank, lo, hi, hist, sums in outs:
+        hist, sums = torch.tensor(hist, dtype=torch.int64), torch.tensor(sums, dtype=torch.float64)
         assert torch.equal(hist, want_hist)                       # integer counts: bit-exact
         torch.testing.assert_close(sums, want_sums, atol=1e-12, rtol=1e-12)
         assert abs(pmdist.global_loss(sums) - 1.25 * float(want_sums[0] / want_sums[1])) < 1e-15

@@ -58,3 +58,32 @@ def test_oracle_vq_microbench():
     np.testing.assert_allclose(z_q[:64], g["z_q_head"], atol=1e-6, rtol=0)
     np.testing.assert_allclose(O.vq_decode_from_indice(ref_idx[:16], E.numpy()), g["dec_head"], atol=1e-6, rtol=0)
     np.testing.assert_allclose(O.vq_top2_gap(z.numpy()[:2048], E.numpy()), g["gap"][:2048], atol=2e-6, rtol=0)
+
+
+# ---- the torch-CPU flavour of the oracle (the timed CPU arm of bench.py) against the same fixtures ----
+def _run_stage1_torch(gold_name):
+    from oracle import paintmind_oracle_torch as OT
+    g = load_golden(gold_name)
+    cfg_name, batch, seed = str(g["cfg_name"]), int(g["batch"]), int(g["seed"])
+    cfg, sd_t, _ = seeded_vqgan(cfg_name, seed)
+    check_weight_checksums(g, sd_t)
+    x = synthetic.make_images(batch, cfg["enc"]["image_size"], seed=seed + 100)
+    with torch.no_grad():
+        z_pre = OT.vqmodel_latent(x, sd_t, cfg)
+        np.testing.assert_allclose(z_pre.numpy(), g["z_pre"], atol=2e-4, rtol=0)
+        z_q, loss, idx = OT.vq_forward(z_pre, sd_t["quantize.embedding.weight"], cfg["beta"])
+        mism = idx.numpy() != g["idx"].astype(np.int64)
+        assert mism.mean() <= 0.002 and np.all(g["gap"][mism] < 1e-4)
+        np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-4)
+        s = int(g["rec_stride"])
+        rec = OT.vqmodel_decode(torch.from_numpy(g["z_q"]), sd_t, cfg).numpy()
+    np.testing.assert_allclose(rec[:, :, ::s, ::s], g["rec_sub"], atol=5e-4, rtol=0)
+    np.testing.assert_allclose(rec.mean(dtype=np.float64), float(g["rec_mean"]), atol=1e-5)
+
+
+def test_torch_oracle_stage1_tiny():
+    _run_stage1_torch("stage1_tiny.npz")
+
+
+def test_torch_oracle_stage1_vit_s():
+    _run_stage1_torch("stage1_vit_s.npz")
