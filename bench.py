@@ -12,7 +12,7 @@ timed region.  Rank 0 prints ONE JSON line.
 
 `--impl reference` times the reference's CPU algorithm for the same path (the torch-CPU oracle port of
 the pure-Python/torch reference: same ATen operators, fp32, all host threads) on a bounded sample of the
-same workload (4 images per step, the reference's own CPU-runnable case, BASELINE configs[0]).
+same workload (16 images per step; BASELINE configs[0] is the same pass at batch 4).
 """
 from __future__ import annotations
 
@@ -46,7 +46,7 @@ def _peaks():
 # CPU arm: the oracle port of the reference algorithm (test infrastructure, used here ONLY as the
 # thing being timed for the cpu_baseline / reference arm — never on the product path)
 # ------------------------------------------------------------------------------------------------
-CPU_SAMPLE = 4      # images per CPU pass = the reference's own CPU-runnable case (BASELINE configs[0]: batch 4, fp32)
+CPU_SAMPLE = 16     # images per CPU pass (BASELINE configs[0] is the same pass at batch 4; 16 keeps all host cores busy)
 
 
 def cpu_reference_images_per_s(sample_batch: int = CPU_SAMPLE, repeats: int = 1, warm: bool = True):
@@ -94,7 +94,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * CPU_SAMPLE / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_step": CPU_SAMPLE,
-                   "note": "bounded sample of the batch-256 workload: each step is one encode+decode pass over 4 images"},
+                   "note": "bounded sample of the batch-256 workload: each step is one encode+decode pass over 16 images"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{CPU_SAMPLE} images per step x {args.steps} steps (torch-CPU fp32 oracle port of the "
                                    f"reference: same ATen operators, {cores} threads)"},
@@ -338,11 +338,49 @@ def run_ours(args):
         e1.record(); torch.cuda.synchronize()
         vq_rate = 65536 * 20 / (e0.elapsed_time(e1) * 1e-3)
 
+    # secondary workload: BASELINE configs[4] — MaskGIT iterative decode, 1024 tokens (reference-faithful),
+    # 12 steps, random text embeddings, global batch 64 batch-sharded over the ranks, final image decoded once
+    maskgit = None
+    if not args.no_maskgit and 64 % world == 0:
+        del model
+        torch.cuda.empty_cache()
+        cfg2 = ver2cfg["paintmindv1"]
+        pipe = pm.create_model(arch="pipeline", version="paintmindv1", pretrained=False)
+        sd2 = {("vqgan." + k): v for k, v in synthetic.make_vqgan_state_dict(cfg, seed=0).items()}
+        sd2.update(synthetic.make_stage2_state_dict(cfg2, cfg, seed=1, context_dim=1024))
+        pipe.load_state_dict(sd2, strict=True)
+        pipe = pipe.to(dev).eval()
+        Bm, T = 64 // world, 12
+        gt = torch.Generator(device=dev).manual_seed(2000 + rank)
+        text = torch.randn(Bm, 77, 1024, device=dev, generator=gt)
+
+        def gen():
+            return pipe.generate(text, timesteps=T, temperature=1.0, topk=5, save_interval=T)   # one decode (step 0)
+
+        gen()
+        barrier()
+        ops.LAUNCHES = 0
+        e0.record()
+        reps = 2
+        for _ in range(reps):
+            gen()
+        e1.record()
+        barrier()
+        tm = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms_gen = float(tm.item())
+        maskgit = {"workload": "MaskGIT generate(): 1024 tokens, 12 steps, topk 5, random text [B,77,1024] (BASELINE configs[4])",
+                   "global_batch": Bm * world, "ms_per_generate": ms_gen, "images_per_s": Bm * world / (ms_gen * 1e-3),
+                   "transformer_tflops_per_gpu": Bm * T * 437.72e9 / (ms_gen * 1e-3) / 1e12,
+                   "gpu_launches_per_generate": ops.LAUNCHES // reps}
+        del pipe
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, secs = cpu_reference_images_per_s(CPU_SAMPLE, repeats=5)
+        v, secs = cpu_reference_images_per_s(2 * CPU_SAMPLE, repeats=4)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{CPU_SAMPLE} images x 5 encode+decode passes (median) of the torch-CPU fp32 oracle port, "
+               "sample": f"{2 * CPU_SAMPLE} images x 4 encode+decode passes (median) of the torch-CPU fp32 oracle port, "
                          f"all host threads ({secs:.1f} s of CPU work)"}
 
     if world > 1:
@@ -358,7 +396,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (201 MB fp32 batch; ~2 GB of activations per step)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kernels, "vq_lookups_per_s": vq_rate,
+            "kernels": kernels, "vq_lookups_per_s": vq_rate, "maskgit": maskgit,
             "check": {"loss": global_loss, "codes_used": used_codes},
         }
         print(json.dumps(line), flush=True)
@@ -373,6 +411,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-maskgit", action="store_true", help="skip the secondary MaskGIT (BASELINE configs[4]) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -188,6 +188,25 @@ typedef struct pm_maskgit_sample_args {
 int pm_maskgit_sample(const pm_maskgit_sample_args* args, void* stream);
 int pm_maskgit_remask(const float* scores, int64_t* ids, int32_t B, int32_t N, int32_t k, int64_t mask_id, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Stage-2 training forward, the pieces around the transformer (generate.py:78-146):
+ *   pm_maskgit_random_mask : Pipeline.random_masking (generate.py:78-108).  Per image the len_keep tokens with the
+ *                            smallest noise keep their latent z[b, i, :32], the others become mask_token;
+ *                            mask[b, i] = 1 where replaced (ties in the noise: lower token index is kept first).
+ *                            noise != NULL injects the uniforms torch.rand(B, N) would have supplied (parity tests);
+ *                            otherwise Philox4x32-10 keyed on (seed, image, token, offset).  x_out may be NULL
+ *                            (mask only).
+ *   pm_ce_label_smooth     : Pipeline.loss (generate.py:110-123): row_loss[i] = mask[i] * cross_entropy(logits[i],
+ *                            label[i], label_smoothing) (rows with mask 0 are skipped, not read); loss_out =
+ *                            sum(row_loss) / sum(mask) reduced in a fixed order in fp64; sums_out[0:2] = the two sums
+ *                            (for a cross-rank all-reduce).  mask == NULL counts every row.
+ * ------------------------------------------------------------------------------------------- */
+int pm_maskgit_random_mask(const float* z, int64_t ldz, const float* noise, uint64_t seed, uint64_t offset,
+                           const float* mask_token, int32_t B, int32_t N, int32_t len_keep, float* mask, float* x_out,
+                           void* stream);
+int pm_ce_label_smooth(const float* logits, int64_t ld, int32_t M, int32_t V, const int64_t* label, const float* mask,
+                       float label_smoothing, float* row_loss, float* loss_out, double* sums_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

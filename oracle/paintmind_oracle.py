@@ -305,3 +305,53 @@ def generate_schedule(timesteps, temperature, num_tokens):
         r = mask_schedule((step + 1) / timesteps)
         out.append((float(r), max(int(r * num_tokens), 1), temperature * (1 - step / timesteps)))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# generate.py (stage-2 TRAINING forward: random_masking / loss / forward, :78-146)
+# --------------------------------------------------------------------------------------------
+def random_masking(x, mask_ratio, mask_token, noise):
+    """Pipeline.random_masking (generate.py:78-108) with the uniform noise injected by the caller.
+    Returns (x with masked rows replaced by mask_token, mask [N, L] fp32, 1 = masked).  Restated literally:
+    argsort -> keep the first len_keep -> append mask tokens -> un-shuffle.  (numpy's stable argsort keeps the
+    lower index first on exact noise ties; torch.argsort leaves that unspecified.)"""
+    N, L, D = x.shape
+    len_mask = max(int(L * mask_ratio), 1)                                  # :86
+    len_keep = L - len_mask                                                 # :87
+    ids_shuffle = np.argsort(noise, axis=1, kind="stable")                  # :92
+    ids_restore = np.argsort(ids_shuffle, axis=1, kind="stable")            # :93
+    ids_keep = ids_shuffle[:, :len_keep]                                    # :95
+    xk = np.take_along_axis(x, ids_keep[..., None], axis=1)                 # :96
+    mt = np.broadcast_to(mask_token.reshape(1, 1, D), (N, L - len_keep, D)) # :97
+    xc = np.concatenate([xk, mt], axis=1)                                   # :98
+    xo = np.take_along_axis(xc, ids_restore[..., None], axis=1)             # :100
+    mask = np.ones((N, L), dtype=F32)                                       # :103
+    mask[:, :len_keep] = 0                                                  # :104
+    mask = np.take_along_axis(mask, ids_restore, axis=1)                    # :106
+    return xo.astype(F32, copy=False), mask
+
+
+def ce_label_smooth_rows(logits2d, label, eps=0.1):
+    """F.cross_entropy(logit, label, label_smoothing=eps, reduction='none') (generate.py:121):
+    (1 - eps) * nll(label) + eps * mean_c(-log p_c)."""
+    m = logits2d.max(axis=-1, keepdims=True)
+    lse = (m[:, 0] + np.log(np.exp(logits2d - m, dtype=F32).sum(axis=-1, dtype=F32))).astype(F32)
+    xy = np.take_along_axis(logits2d, label[:, None], axis=-1)[:, 0]
+    return (lse - F32(1.0 - eps) * xy - F32(eps) * logits2d.mean(axis=-1, dtype=F32)).astype(F32)
+
+
+def masked_ce_loss(logits, label, masks, eps=0.1):
+    """Pipeline.loss (generate.py:110-123)."""
+    V = logits.shape[-1]
+    rows = ce_label_smooth_rows(logits.reshape(-1, V), label.reshape(-1), eps)
+    mk = masks.reshape(-1).astype(F32)
+    return F32((rows * mk).sum(dtype=np.float64) / mk.sum(dtype=np.float64))
+
+
+def pipeline_train_forward(img, text, mask_ratio, noise, sd, cfg2, cfg1):
+    """Pipeline.forward (generate.py:136-146): to_latent -> random_masking -> tokens2logits -> loss."""
+    sd1 = {k[len("vqgan."):]: v for k, v in sd.items() if k.startswith("vqgan.")}
+    z_q, _, ids = vqmodel_encode(img, sd1, cfg1)                                    # :138 (to_latent, :125-131)
+    xm, mask = random_masking(z_q, mask_ratio, sd["mask_token"], noise)             # :140
+    logits = cond_transformer_forward(xm, text, sd, cfg2)                           # :142
+    return masked_ce_loss(logits, ids, mask), ids, mask, logits                     # :144

@@ -103,6 +103,8 @@ EXPORTS = {
     "pm_cast_f32_bf16": [_p, _p, _i64, _p],
     "pm_maskgit_sample": [C.POINTER(MaskgitSampleArgs), _p],
     "pm_maskgit_remask": [_p, _p, _i32, _i32, _i32, _i64, _p],
+    "pm_maskgit_random_mask": [_p, _i64, _p, C.c_uint64, C.c_uint64, _p, _i32, _i32, _i32, _p, _p, _p],
+    "pm_ce_label_smooth": [_p, _i64, _i32, _i32, _p, _p, _f, _p, _p, _p, _p],
 }
 
 

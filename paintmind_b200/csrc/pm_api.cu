@@ -134,6 +134,19 @@ int pm_maskgit_remask(const float* scores, int64_t* ids, int32_t B, int32_t N, i
   return pm_maskgit_remask_launch(scores, reinterpret_cast<long long*>(ids), B, N, k, mask_id, static_cast<cudaStream_t>(stream));
 }
 
+int pm_maskgit_random_mask(const float* z, int64_t ldz, const float* noise, uint64_t seed, uint64_t offset,
+                           const float* mask_token, int32_t B, int32_t N, int32_t len_keep, float* mask, float* x_out,
+                           void* stream) {
+  return pm_maskgit_random_mask_launch(z, ldz, noise, seed, offset, mask_token, B, N, len_keep, mask, x_out,
+                                       static_cast<cudaStream_t>(stream));
+}
+
+int pm_ce_label_smooth(const float* logits, int64_t ld, int32_t M, int32_t V, const int64_t* label, const float* mask,
+                       float label_smoothing, float* row_loss, float* loss_out, double* sums_out, void* stream) {
+  return pm_ce_label_smooth_launch(logits, ld, M, V, reinterpret_cast<const long long*>(label), mask, label_smoothing,
+                                   row_loss, loss_out, sums_out, static_cast<cudaStream_t>(stream));
+}
+
 int pm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   return pm_cast_launch(src, dst, n, static_cast<cudaStream_t>(stream));
 }

@@ -75,6 +75,11 @@ int pm_num_sms();
 int pm_cast_launch(const float* src, void* dst, long long n, cudaStream_t stream);
 int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream);
 int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, cudaStream_t stream);
+int pm_maskgit_random_mask_launch(const float* z, int64_t ldz, const float* noise, unsigned long long seed,
+                                  unsigned long long offset, const float* mask_token, int B, int N, int len_keep,
+                                  float* mask, float* x_out, cudaStream_t stream);
+int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, const long long* label, const float* mask,
+                              float eps, float* row_loss, float* loss_out, double* sums_out, cudaStream_t stream);
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
 int pm_vq_codebook_prep_launch(const float* E, int n_e, float* en, void* packed, cudaStream_t stream);
 int pm_vq_launch(const VqParams& p, cudaStream_t stream);

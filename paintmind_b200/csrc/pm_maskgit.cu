@@ -364,6 +364,177 @@ maskgit_remask_kernel(const float* __restrict__ scores, long long* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stage-2 TRAINING forward, the two pieces around the transformer:
+//
+// random_masking (generate.py:78-108): per image, the len_keep tokens with the SMALLEST noise keep their latent,
+// the others are replaced by mask_token; mask = 1 where replaced.  The reference does argsort(noise) ->
+// gather -> cat(mask tokens) -> gather(ids_restore); the result is the same as ranking every token:
+//   rank_i = #{j : n_j < n_i or (n_j == n_i and j < i)};  masked_i = rank_i >= len_keep.
+// One block per image; noise comes from the caller (parity tests) or Philox keyed on (seed, image, token, offset).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+maskgit_random_mask_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ noise,
+                           unsigned long long seed, unsigned long long offset, const float* __restrict__ mask_token,
+                           int N, int len_keep, float* __restrict__ mask, float* __restrict__ x_out) {
+  extern __shared__ float sm_noise[];                 // [N] noise, then [N] flags
+  float* flag = sm_noise + N;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    sm_noise[i] = noise != nullptr ? noise[static_cast<size_t>(b) * N + i]
+                                   : philox_uniform(seed, static_cast<uint32_t>(b), static_cast<uint32_t>(i), static_cast<uint32_t>(offset));
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float ni = sm_noise[i];
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < N; ++j) {
+      const float nj = sm_noise[j];                   // broadcast read
+      rank += (nj < ni || (nj == ni && j < i)) ? 1 : 0;
+    }
+    const float m = rank >= len_keep ? 1.0f : 0.0f;
+    flag[i] = m;
+    mask[static_cast<size_t>(b) * N + i] = m;
+  }
+  __syncthreads();
+  if (x_out == nullptr) return;
+  // tokens: 8 threads per 32-float row (16 B each), coalesced
+  for (int e = threadIdx.x; e < N * 8; e += blockDim.x) {
+    const int i = e >> 3, c = (e & 7) * 4;
+    const size_t row = static_cast<size_t>(b) * N + i;
+    const float4 v = flag[i] != 0.0f ? *reinterpret_cast<const float4*>(mask_token + c)
+                                     : *reinterpret_cast<const float4*>(z + row * ldz + c);
+    *reinterpret_cast<float4*>(x_out + row * 32 + c) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Masked label-smoothed cross entropy (generate.py:110-123: F.cross_entropy(logit, label, label_smoothing = eps,
+// reduction = 'none'), then (loss * masks).sum() / masks.sum()).  Per row
+//   loss = (1 - eps) * (lse - x[label]) + eps * (lse - mean(x)) = lse - (1 - eps) * x[label] - eps * mean(x)
+// One warp streams one fp32 logit row ONCE (8 x 16-byte loads in flight per lane): online max / sum-exp2 / sum.
+// Rows with mask == 0 contribute nothing to the reference's result and are not read at all (at mask_ratio 0.75
+// that is a quarter of the 4*M*V bytes).  row_loss[row] = loss * mask; a single-block second kernel reduces
+// row_loss and mask in a fixed order in fp64 (deterministic) and forms the scalar.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const float* __restrict__ logits, int64_t ld, int M, int V, const long long* __restrict__ label,
+               const float* __restrict__ mask, float eps, float* __restrict__ row_loss) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float mk = mask != nullptr ? mask[row] : 1.0f;
+  if (mk == 0.0f) {
+    if (lane == 0) row_loss[row] = 0.0f;
+    return;
+  }
+  const float4* x4 = reinterpret_cast<const float4*>(logits + static_cast<size_t>(row) * ld);
+  const int nvec = V >> 2;
+  constexpr float L2E = 1.4426950408889634f;
+  float m = -INFINITY, s = 0.0f, t = 0.0f;            // lane-local: running max, sum exp(x - m), sum x
+  for (int c0 = lane; c0 < nvec; c0 += 32 * 8) {
+    float4 q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + u * 32;
+      q[u] = c < nvec ? __ldcs(x4 + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float cm = m;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cm = fmaxf(cm, fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w)));
+    if (cm > m) {
+      s *= exp2f((m - cm) * L2E);                     // m = -inf: s is 0 anyway
+      m = cm;
+    }
+    const float nm = -m * L2E;
+    float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f}, pt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u * 32 < nvec) {
+        const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float ex;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(e[k], L2E, nm)));
+          ps[k] += ex;
+          pt[k] += e[k];
+        }
+      }
+    }
+    s += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    t += (pt[0] + pt[1]) + (pt[2] + pt[3]);
+  }
+  float mw = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+  float sw = (m == -INFINITY) ? 0.0f : s * exp2f((m - mw) * L2E);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  if (lane == 0) {
+    const long long y = label[row];
+    const float xy = (y >= 0 && y < V) ? logits[static_cast<size_t>(row) * ld + y] : 0.0f;
+    const float lse = mw + logf(sw);
+    row_loss[row] = (lse - (1.0f - eps) * xy - eps * (t / static_cast<float>(V))) * mk;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+ce_reduce_kernel(const float* __restrict__ row_loss, const float* __restrict__ mask, int M, float* __restrict__ loss_out,
+                 double* __restrict__ sums_out) {
+  __shared__ double sh_l[1024], sh_m[1024];
+  double al = 0.0, am = 0.0;
+  for (int i = threadIdx.x; i < M; i += 1024) {       // fixed assignment and order: deterministic
+    al += static_cast<double>(row_loss[i]);
+    am += mask != nullptr ? static_cast<double>(mask[i]) : 1.0;
+  }
+  sh_l[threadIdx.x] = al;
+  sh_m[threadIdx.x] = am;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh_l[threadIdx.x] += sh_l[threadIdx.x + o];
+      sh_m[threadIdx.x] += sh_m[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (loss_out != nullptr) *loss_out = static_cast<float>(sh_l[0] / sh_m[0]);     // masks.sum() == 0 -> nan, as the reference
+    if (sums_out != nullptr) {
+      sums_out[0] = sh_l[0];
+      sums_out[1] = sh_m[0];
+    }
+  }
+}
+
+int pm_maskgit_random_mask_launch(const float* z, int64_t ldz, const float* noise, unsigned long long seed,
+                                  unsigned long long offset, const float* mask_token, int B, int N, int len_keep,
+                                  float* mask, float* x_out, cudaStream_t stream) {
+  if (mask == nullptr || B <= 0 || N <= 0 || N > 12288 || len_keep < 0 || len_keep > N) return PM_ERR_INVALID;
+  if (x_out != nullptr && (z == nullptr || mask_token == nullptr || (ldz % 4) != 0)) return PM_ERR_INVALID;
+  const int threads = N < 1024 ? ((N + 31) / 32) * 32 : 1024;
+  maskgit_random_mask_kernel<<<B, threads, 2 * N * sizeof(float), stream>>>(z, ldz, noise, seed, offset, mask_token, N,
+                                                                            len_keep, mask, x_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, const long long* label, const float* mask,
+                              float eps, float* row_loss, float* loss_out, double* sums_out, cudaStream_t stream) {
+  if (logits == nullptr || label == nullptr || row_loss == nullptr || M <= 0 || V <= 0 || (V & 3) != 0 || (ld & 3) != 0)
+    return PM_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(logits) & 15) != 0) return PM_ERR_INVALID;
+  ce_rows_kernel<<<(M + 7) / 8, 256, 0, stream>>>(logits, ld, M, V, label, mask, eps, row_loss);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (loss_out != nullptr || sums_out != nullptr) {
+    ce_reduce_kernel<<<1, 1024, 0, stream>>>(row_loss, mask, M, loss_out, sums_out);
+    e = cudaGetLastError();
+  }
+  return static_cast<int>(e);
+}
+
 int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
   if (p.logits == nullptr || p.M <= 0 || p.V <= 0 || (p.V & 3) != 0 || (p.ld & 3) != 0) return PM_ERR_INVALID;
   if (p.topk < 1 || p.topk > 32 || p.topk > p.V) return PM_ERR_INVALID;

@@ -2,10 +2,12 @@
 :148-198) on the CUDA kernels.  Same constructor, attributes (vqgan, text_model, transformer,
 mask_token, mask_token_id, image_size, patch_size, num_tokens) and method signatures.
 
-Out of scope here: the T5 text encoder (frozen third-party model, needs network
+The stage-2 training FORWARD (random_masking / loss / forward, generate.py:78-146)
+is also here as forward values (no autograd graph).
+
+Out of scope: the T5 text encoder (frozen third-party model, needs network
 weights — `text_model` is a pluggable callable, by default seeded random embeddings as in BASELINE
-config 5), the training forward (random_masking / loss / forward) and inpaint / outpaint (broken as
-shipped in the reference).
+config 5), backward passes, and inpaint / outpaint (broken as shipped in the reference).
 """
 from __future__ import annotations
 
@@ -66,15 +68,67 @@ class Pipeline(nn.Module):
     def from_pretrained(self, path):
         return self.load_state_dict(torch.load(path))
 
-    # ---- training-time members of the reference: out of scope --------------------------------
-    def random_masking(self, x, mask_ratio):
-        raise NotImplementedError("training-time masking (generate.py:78-108) is out of scope of the inference hot path")
+    # ---- stage-2 training FORWARD (generate.py:78-146) -------------------
+    # Forward values only: like every other entry point of this package the result carries no autograd graph
+    # (the backward pass of the transformer is out of scope).
+    @torch.no_grad()
+    def random_masking(self, x, mask_ratio, _noise=None):
+        """generate.py:78-108 -> (x with masked rows replaced by mask_token, mask [N, L] fp32 with 1 = masked).
+        `_noise` injects the [N, L] uniforms the reference draws with torch.rand (parity tests); production
+        draws Philox4x32-10 keyed on (torch.initial_seed(), sample, token, call counter)."""
+        if not x.is_cuda:
+            raise RuntimeError("paintmind_b200: CUDA only (no CPU fallback)")
+        N, L, D = x.shape
+        if D != 32:
+            raise RuntimeError("paintmind_b200 token kernels are built for 32-d tokens")
+        len_mask = max(int(L * mask_ratio), 1)
+        len_keep = L - len_mask
+        x2d = x.detach().reshape(N * L, D)
+        if x2d.dtype != torch.float32:
+            x2d = x2d.float()
+        if x2d.stride(1) != 1 or x2d.stride(0) % 4 != 0 or x2d.data_ptr() % 16 != 0:
+            x2d = x2d.contiguous()
+        mask = torch.empty(N, L, device=x.device, dtype=torch.float32)
+        out = torch.empty(N * L, D, device=x.device, dtype=torch.float32)
+        if self._rng_seed is None:
+            self._rng_seed = torch.initial_seed()
+        self._rng_calls += 1
+        noise = None
+        if _noise is not None:
+            noise = _noise.to(device=x.device, dtype=torch.float32).contiguous()
+            if noise.shape != (N, L):
+                raise RuntimeError(f"_noise must be [{N}, {L}]")
+        ops.maskgit_random_mask(x2d, self.mask_token.detach().float().contiguous().view(-1), N, L, len_keep,
+                                mask=mask, x_out=out, noise=noise, seed=self._rng_seed, offset=self._rng_calls)
+        return out.view(N, L, D), mask
 
+    @torch.no_grad()
     def loss(self, logit, label, masks):
-        raise NotImplementedError("training loss (generate.py:110-123) is out of scope of the inference hot path")
+        """generate.py:110-123: label-smoothed (0.1) cross entropy averaged over the masked positions."""
+        if not logit.is_cuda:
+            raise RuntimeError("paintmind_b200: CUDA only (no CPU fallback)")
+        B, L, V = logit.shape
+        lg = logit.detach().reshape(B * L, V)
+        if lg.dtype != torch.float32:
+            lg = lg.float()
+        if lg.stride(1) != 1 or lg.stride(0) % 4 != 0 or lg.data_ptr() % 16 != 0:
+            lg = lg.contiguous()
+        lab = label.reshape(-1).to(torch.int64).contiguous()
+        mk = masks.reshape(-1).to(torch.float32).contiguous()
+        row_loss = torch.empty(B * L, device=logit.device, dtype=torch.float32)
+        out = torch.empty((), device=logit.device, dtype=torch.float32)
+        sums = torch.empty(2, device=logit.device, dtype=torch.float64)
+        ops.ce_label_smooth(lg, lab, mk, 0.1, row_loss=row_loss, loss_out=out, sums_out=sums)
+        self._last_loss_sums = sums          # (sum of masked row losses, mask count): all-reduce these across ranks
+        return out
 
-    def forward(self, img, text=None, mask_ratio=0.75):
-        raise NotImplementedError("the stage-2 training forward (generate.py:136-146) is out of scope; use generate()/sample()")
+    @torch.no_grad()
+    def forward(self, img, text=None, mask_ratio=0.75, _noise=None):
+        """generate.py:136-146: tokenize (frozen VQGAN) -> random masking -> transformer -> masked CE."""
+        x, ids, text = self.to_latent(img, text)
+        x, mask = self.random_masking(x, mask_ratio, _noise=_noise)
+        logits = self.tokens2logits(x, text)
+        return self.loss(logits, ids, mask)
 
     def inpaint(self, *a, **k):
         raise NotImplementedError("inpaint is broken as shipped in the reference (float ids, generate.py:206-210) and out of scope")

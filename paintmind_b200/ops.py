@@ -221,3 +221,25 @@ def cast_bf16(src, dst):
     _lib.check(_lib.load().pm_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "pm_cast_f32_bf16")
     _prof_end(t0, ("cast_bf16", src.numel()))
     return dst
+
+
+def maskgit_random_mask(z2d, mask_token, B, N, len_keep, *, mask, x_out=None, noise=None, seed=0, offset=0):
+    """Pipeline.random_masking (generate.py:78-108): mask [B, N] fp32 (1 = replaced) and the masked token rows."""
+    _require_cuda(mask)
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_maskgit_random_mask(_ptr(z2d), z2d.stride(0) if z2d is not None else 0, _ptr(noise),
+                                                  int(seed) & (2 ** 64 - 1), int(offset), _ptr(mask_token), B, N,
+                                                  int(len_keep), _ptr(mask), _ptr(x_out), _stream()),
+               "pm_maskgit_random_mask")
+    _prof_end(t0, ("maskgit_random_mask", B, N))
+
+
+def ce_label_smooth(logits2d, label, mask, label_smoothing, *, row_loss, loss_out=None, sums_out=None):
+    """Masked label-smoothed cross entropy (generate.py:110-123) over fp32 logits [M, V]."""
+    _require_cuda(logits2d, label, row_loss)
+    M, V = logits2d.shape
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_ce_label_smooth(_ptr(logits2d), logits2d.stride(0), M, V, _ptr(label), _ptr(mask),
+                                              float(label_smoothing), _ptr(row_loss), _ptr(loss_out), _ptr(sums_out),
+                                              _stream()), "pm_ce_label_smooth")
+    _prof_end(t0, ("ce_label_smooth", M, V))

@@ -9,7 +9,7 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json
 tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 if [ "${2:-full}" = "full" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 270 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-maskgit > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bench.log
 # 4th gemm launch of a step = layer-0 w12 (SwiGLU epilogue); 2nd = qkv (LN fold)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 3 -c 1 -o gpurun_out/${TAG}_swiglu -f \

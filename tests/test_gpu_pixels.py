@@ -15,9 +15,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _reference_ingest(u8_nhwc):
-    """ToTensor + Normalize(mean 0.5, std 0.5) exactly as torchvision evaluates them (fp32)."""
-    t = u8_nhwc.permute(0, 3, 1, 2).to(torch.float32).div(255)
-    return t.sub(0.5).div(0.5)
+    """ToTensor + Normalize(mean 0.5, std 0.5) exactly as torchvision evaluates them: fp32 ON THE HOST (the
+    transform runs in the data loader; torch's CPU `div` is a true division, whereas its CUDA kernel multiplies by
+    the rounded reciprocal of a scalar divisor and differs in the last bit for some byte values)."""
+    dev = u8_nhwc.device
+    t = u8_nhwc.cpu().permute(0, 3, 1, 2).to(torch.float32).div(255)
+    return t.sub(0.5).div(0.5).contiguous().to(dev)
 
 
 def _reference_restore(x_nchw):
