@@ -279,49 +279,65 @@ def run_ours(args):
     # step i (double-buffered device input; every step still moves its own 201 MB in and 203 MB out).
     main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    xd = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
-    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def run_e2e(n):
-        with torch.cuda.stream(s_in):
-            xd[0].copy_(x_host, non_blocking=True)
-            ev_in[0].record(s_in)
-        for i in range(n):
-            cur = i & 1
-            if i + 1 < n:
-                with torch.cuda.stream(s_in):
-                    if i >= 1:
-                        s_in.wait_event(ev_free[1 - cur])       # step i-1 no longer reads that input buffer
-                    xd[1 - cur].copy_(x_host, non_blocking=True)
-                    ev_in[1 - cur].record(s_in)
-            main.wait_event(ev_in[cur])
-            z, loss, idx = model.encode(xd[cur])
-            ev_free[cur].record(main)
-            rec = model.decode(z)
-            ev_c = torch.cuda.Event()
-            ev_c.record(main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_c)
-                rec_host.copy_(rec, non_blocking=True)
-                idx_host.copy_(idx, non_blocking=True)
-                loss_host.copy_(loss, non_blocking=True)
-                for t in (rec, idx, loss):
-                    t.record_stream(s_out)
-        main.wait_stream(s_out)
+    def make_e2e(x_host, rec_host, encode, decode):
+        xd = [torch.empty(x_host.shape, dtype=x_host.dtype, device=dev) for _ in range(2)]
+        ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_free = [torch.cuda.Event(), torch.cuda.Event()]
 
-    run_e2e(2)
-    barrier()
-    e0.record()
-    run_e2e(K)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / (float(t.item()) * 1e-3)
+        def run(n):
+            with torch.cuda.stream(s_in):
+                xd[0].copy_(x_host, non_blocking=True)
+                ev_in[0].record(s_in)
+            for i in range(n):
+                cur = i & 1
+                if i + 1 < n:
+                    with torch.cuda.stream(s_in):
+                        if i >= 1:
+                            s_in.wait_event(ev_free[1 - cur])       # step i-1 no longer reads that input buffer
+                        xd[1 - cur].copy_(x_host, non_blocking=True)
+                        ev_in[1 - cur].record(s_in)
+                main.wait_event(ev_in[cur])
+                z, loss, idx = encode(xd[cur])
+                ev_free[cur].record(main)
+                rec = decode(z)
+                ev_c = torch.cuda.Event()
+                ev_c.record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_c)
+                    rec_host.copy_(rec, non_blocking=True)
+                    idx_host.copy_(idx, non_blocking=True)
+                    loss_host.copy_(loss, non_blocking=True)
+                    for t in (rec, idx, loss):
+                        t.record_stream(s_out)
+            main.wait_stream(s_out)
+        return run
+
+    def time_e2e(run):
+        run(2)
+        barrier()
+        e0.record()
+        run(K)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * K / (float(t.item()) * 1e-3)
+
+    e2e_value = time_e2e(make_e2e(x_host, rec_host, model.encode, model.decode))
     h2d = x_host.numel() * 4
     d2h = rec_host.numel() * 4 + idx_host.numel() * 8 + 4
+
+    # the same loop fed with decoded pixels and returning pixels (uint8 NHWC both ways): the
+    # ToTensor/Normalize ingest and the `restore` egress of the reference run fused inside the first / last kernel
+    px_host = torch.empty(B, 256, 256, 3, dtype=torch.uint8, pin_memory=True)
+    px_host.copy_(((x_dev.permute(0, 2, 3, 1) + 1) * 127.5).clamp_(0, 255).to(torch.uint8))
+    pxo_host = torch.empty(B, 256, 256, 3, dtype=torch.uint8, pin_memory=True)
+    e2e_px = time_e2e(make_e2e(px_host, pxo_host, model.encode_pixels, model.decode_pixels))
+    e2e_pixels = {"value": e2e_px, "unit": UNIT, "h2d_bytes_per_step": px_host.numel(),
+                  "d2h_bytes_per_step": pxo_host.numel() + idx_host.numel() * 8 + 4,
+                  "api": "VQModel.encode_pixels / decode_pixels (uint8 NHWC in and out)"}
 
     vq_rate = None
     if rank == 0:
@@ -395,6 +411,7 @@ def run_ours(args):
                        "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of usage histogram + loss sums",
                        "l2": "inputs larger than L2 (201 MB fp32 batch; ~2 GB of activations per step)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_pixels": e2e_pixels,
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "vq_lookups_per_s": vq_rate, "maskgit": maskgit,
             "check": {"loss": global_loss, "codes_used": used_codes},

@@ -33,8 +33,10 @@ extern "C" {
 /* output modes of pm_gemm_bf16 */
 #define PM_OUT_BF16 0    /* bf16 row-major [M, N] (or [M, N/2] with swiglu) via TMA store      */
 #define PM_OUT_F32 1     /* fp32 row-major [M, N]                                              */
-#define PM_OUT_UNPATCH 2 /* fp32 NCHW image, clamp(-1,1): layers.py:150 + vqmodel.py:30        */
-#define PM_OUT_UNPATCH_U8 3 /* uint8 NHWC pixels: the same + `restore` (reconstruct.py:11-16):
+#define PM_OUT_UNPATCH 2 /* fp32 NCHW image, clamp(-1,1): layers.py:150 + vqmodel.py:30; patch 8; the rows of W
+                            (and bias / colsum) must be permuted from the reference's (p1 p2 c) order to
+                            (c p1 p2) so that 8 consecutive columns are 8 consecutive pixels               */
+#define PM_OUT_UNPATCH_U8 3 /* uint8 NHWC pixels, W rows in the reference's (p1 p2 c) order: + `restore` (reconstruct.py:11-16):
                                u = uint8(255 * ((clamp(v,-1,1) + 1) * 0.5)), patch 8, 3 channels  */
 
 /* Library / device introspection. */
@@ -83,6 +85,9 @@ typedef struct pm_gemm_args {
   int32_t cta_group;    /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pairs: tcgen05.mma.cta_group::2
                            on 256 x 256 tiles (needs bn == 256)                                        */
   int64_t* debug;       /* optional [grid, 4] int64 stall counters of the MMA issuer (profiling aid) or NULL      */
+  int32_t res_mod;      /* 0: `res` is [M, N_out].  > 0 (multiple of 128): `res` is a [res_mod, N_out] bf16 table and
+                           output row r adds res[r % res_mod] — the position embedding (layers.py:108,146;
+                           transformer.py:82) staged through shared memory by TMA instead of per-thread fp32 loads */
 } pm_gemm_args;
 
 int pm_gemm_bf16(const pm_gemm_args* args, void* stream);

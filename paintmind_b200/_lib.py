@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
         ("pos_rows", C.c_int32), ("out_mode", C.c_int32), ("swiglu", C.c_int32), ("bn", C.c_int32),
         ("patch", C.c_int32), ("channels", C.c_int32), ("grid", C.c_int32), ("max_ctas", C.c_int32),
         ("stats_raw", C.c_int32), ("ln_eps", C.c_float), ("stats_out", C.c_void_p),
-        ("cta_group", C.c_int32), ("debug", C.c_void_p),
+        ("cta_group", C.c_int32), ("debug", C.c_void_p), ("res_mod", C.c_int32),
     ]
 
 

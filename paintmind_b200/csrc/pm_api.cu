@@ -49,6 +49,7 @@ int pm_gemm_bf16(const pm_gemm_args* a, void* stream) {
   // M = 262144, single vs pair: qkv 0.389 / 0.352 ms, out 0.163 / 0.158, w12+SwiGLU 0.652 / 0.602, w3 0.357 / 0.319.
   p.cta_pair = a->cta_group == 1 ? 0 : 1;
   p.debug = reinterpret_cast<long long*>(a->debug);
+  p.res_mod = a->res_mod;
   if ((p.colsum == nullptr) != (p.stats == nullptr)) return PM_ERR_INVALID;
   int bn = a->bn;
   if (bn == 0) {

@@ -26,6 +26,8 @@ struct GemmParams {
   int stats_raw;      // 1: `stats` holds raw (sum, sum of squares) over K columns; 0: (mean, rstd)
   float ln_eps;
   long long* debug;   // optional [grid, 4] int64: MMA-issuer stall cycles (accumulator wait, operand wait, total, k_blocks)
+  int res_mod;        // > 0: `res` has res_mod rows and row r of the output adds res[r % res_mod] (a broadcast table such as
+                      // the position embedding, staged by TMA like a residual); multiple of 128
   int cta_pair;       // 1: use the cta_group::2 kernel (256-row tiles) when the tile shape allows it
 };
 

@@ -13,6 +13,8 @@
 #include "pm_common.cuh"
 #include "pm_kernels.h"
 
+#include <stdlib.h>
+
 namespace pm {
 
 // ---------------------------------------------------------------------------------------------
@@ -342,6 +344,249 @@ maskgit_sample_smem_kernel(const MaskgitParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Block-per-row variant of the staged kernel (V % 512 == 0, row <= 64 KB): FOUR warps share one row buffer, so an SM
+// holds 6 rows in flight with 24 warps instead of 6 — the one-warp-per-row kernel above is latency-bound on its two
+// passes (3.0 TB/s = 47 % of the HBM copy peak at V = 8192), not on HBM.  Per row:
+//   TMA bulk copy -> pass 1 (per-thread two largest, per-warp k-th largest leader; tau = the best of the four
+//   lower bounds) -> pass 2 (sum exp, candidates >= tau into per-warp lists, warp-aggregated appends in a fixed
+//   order) -> warp 0 selects the exact top-k (value desc, index asc), applies the gumbel arg-max and writes.
+// If a candidate list overflows (rows with thousands of equal values) the block falls back to k rounds of a
+// block-wide arg-max over the staged row: results never depend on the capacity.
+// ---------------------------------------------------------------------------------------------
+constexpr int MGB_WARPS = 4;
+constexpr int MGB_CAND = 64;      // per warp
+
+__global__ void __launch_bounds__(MGB_WARPS * 32)
+maskgit_sample_block_kernel(const MaskgitParams p) {
+  extern __shared__ __align__(128) uint8_t mg_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_bytes = p.V * 4;
+  float* buf = reinterpret_cast<float*>(mg_smem);
+  uint8_t* tail = mg_smem + row_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  float* sh_f = reinterpret_cast<float*>(tail + 16);                 // [0..3] warp max, [4..7] warp tau, [8..11] warp sum
+  int* sh_n = reinterpret_cast<int*>(tail + 64);                     // [0..3] candidates per warp
+  float* cand_v = reinterpret_cast<float*>(tail + 128);              // [4][MGB_CAND]
+  int* cand_i = reinterpret_cast<int*>(tail + 128 + MGB_WARPS * MGB_CAND * 4);
+  float* sel_v = reinterpret_cast<float*>(tail + 128 + MGB_WARPS * MGB_CAND * 8);          // [32] slow-path winners
+  int* sel_i = reinterpret_cast<int*>(tail + 128 + MGB_WARPS * MGB_CAND * 8 + 128);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int k = p.topk;
+  const int nvec = p.V >> 2;                                         // multiple of 128
+  const float4* b4 = reinterpret_cast<const float4*>(buf);
+  uint32_t phase = 0;
+  for (int row = blockIdx.x; row < p.M; row += gridDim.x) {
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(bar, static_cast<uint32_t>(row_bytes));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(buf)), "l"(reinterpret_cast<uint64_t>(p.logits + static_cast<size_t>(row) * p.ld)),
+                   "r"(static_cast<uint32_t>(row_bytes)), "r"(smem_u32(bar))
+                   : "memory");
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    // ---- pass 1: per-thread two largest values ----
+    float t0 = -INFINITY, t1 = -INFINITY;
+    for (int c = threadIdx.x; c < nvec; c += MGB_WARPS * 32 * 4) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = b4[c + MGB_WARPS * 32 * u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          t1 = fmaxf(t1, fminf(t0, e[t]));
+          t0 = fmaxf(t0, e[t]);
+        }
+      }
+    }
+    float mw = t0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    // k-th largest of this warp's 64 leaders: a lower bound of the row's k-th largest value
+    float a0 = t0, a1 = t1, tau_w = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      float bv = a0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bv = fmaxf(bv, __shfl_xor_sync(0xffffffffu, bv, o));
+      tau_w = bv;
+      const unsigned who = __ballot_sync(0xffffffffu, a0 == bv);
+      if (lane == __ffs(who) - 1) { a0 = a1; a1 = -INFINITY; }
+    }
+    if (lane == 0) {
+      sh_f[warp] = mw;
+      sh_f[4 + warp] = tau_w;
+    }
+    __syncthreads();
+    const float m_row = fmaxf(fmaxf(sh_f[0], sh_f[1]), fmaxf(sh_f[2], sh_f[3]));
+    const float tau = fmaxf(fmaxf(sh_f[4], sh_f[5]), fmaxf(sh_f[6], sh_f[7]));
+    // ---- pass 2: softmax denominator and candidates >= tau ----
+    float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    int ncand = 0;                                                    // warp-uniform
+    float* cv_w = cand_v + warp * MGB_CAND;
+    int* ci_w = cand_i + warp * MGB_CAND;
+    const float nm = -m_row * 1.4426950408889634f;
+    for (int c = threadIdx.x; c < nvec; c += MGB_WARPS * 32 * 4) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = b4[c + MGB_WARPS * 32 * u];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float ex;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(e[t], 1.4426950408889634f, nm)));
+          ps[u] += ex;
+          any |= (e[t] >= tau);
+        }
+      }
+      if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const bool hit = e[t] >= tau;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+              const int pos = ncand + __popc(m & ((1u << lane) - 1u));
+              if (pos < MGB_CAND) { cv_w[pos] = e[t]; ci_w[pos] = (c + MGB_WARPS * 32 * u) * 4 + t; }
+            }
+            ncand += __popc(m);
+          }
+        }
+      }
+    }
+    float ssum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    if (lane == 0) {
+      sh_f[8 + warp] = ssum;
+      sh_n[warp] = ncand;
+    }
+    __syncthreads();
+    const bool overflow = sh_n[0] > MGB_CAND || sh_n[1] > MGB_CAND || sh_n[2] > MGB_CAND || sh_n[3] > MGB_CAND;
+    if (overflow) {
+      // degenerate row (masses of equal values): k rounds of a block-wide arg-max over the staged row, each round
+      // taking the successor of the previous pick in (value desc, index asc) order — capacity-independent, few registers
+      float pv = INFINITY;
+      int pi = -1;
+      for (int r = 0; r < k; ++r) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = threadIdx.x; c < nvec; c += MGB_WARPS * 32) {
+          const float4 qq = b4[c];
+          const float e[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int idx = c * 4 + t;
+            const bool after = e[t] < pv || (e[t] == pv && idx > pi);
+            if (after && (e[t] > bv || (e[t] == bv && idx < bi))) { bv = e[t]; bi = idx; }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { cand_v[warp] = bv; cand_i[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float fv = cand_v[0];
+          int fi = cand_i[0];
+          for (int w = 1; w < MGB_WARPS; ++w)
+            if (cand_v[w] > fv || (cand_v[w] == fv && cand_i[w] < fi)) { fv = cand_v[w]; fi = cand_i[w]; }
+          sel_v[r] = fv;
+          sel_i[r] = fi;
+        }
+        __syncthreads();
+        pv = sel_v[r];
+        pi = sel_i[r];
+      }
+    }
+    if (warp == 0) {
+      const float s_row = (sh_f[8] + sh_f[9]) + (sh_f[10] + sh_f[11]);       // fixed order: deterministic
+      float my_v = -INFINITY;
+      int my_i = 0x7fffffff;
+      if (!overflow) {
+        // exact top-k among <= 256 candidates (value desc, index asc); lane r keeps winner r
+        float cv[2 * MGB_WARPS];
+        int ci[2 * MGB_WARPS];
+#pragma unroll
+        for (int w = 0; w < MGB_WARPS; ++w)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = h * 32 + lane;
+            const bool ok = j < sh_n[w];
+            cv[w * 2 + h] = ok ? cand_v[w * MGB_CAND + j] : -INFINITY;
+            ci[w * 2 + h] = ok ? cand_i[w * MGB_CAND + j] : 0x7fffffff;
+          }
+        for (int r = 0; r < k; ++r) {
+          float bv = -INFINITY;
+          int bi = 0x7fffffff;
+#pragma unroll
+          for (int u = 0; u < 2 * MGB_WARPS; ++u)
+            if (cv[u] > bv || (cv[u] == bv && ci[u] < bi)) { bv = cv[u]; bi = ci[u]; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+#pragma unroll
+          for (int u = 0; u < 2 * MGB_WARPS; ++u)
+            if (ci[u] == bi) { cv[u] = -INFINITY; ci[u] = 0x7fffffff; }
+          if (lane == r) { my_v = bv; my_i = bi; }
+        }
+      } else if (lane < k) {
+        my_v = sel_v[lane];
+        my_i = sel_i[lane];
+      }
+      // ---- gumbel-perturbed arg-max over the k survivors (generate.py:45-46) ----
+      float score = -INFINITY;
+      if (lane < k && my_i != 0x7fffffff) {
+        float u;
+        if (p.noise != nullptr) u = p.noise[static_cast<size_t>(row) * p.ld_noise + my_i];
+        else u = philox_uniform(p.seed, static_cast<uint32_t>(row), static_cast<uint32_t>(my_i), static_cast<uint32_t>(p.offset));
+        const float inner = -logf(fmaxf(u, 1e-20f));
+        const float g = -logf(fmaxf(inner, 1e-20f));
+        score = my_v / fmaxf(p.temperature, 1e-10f) + g;
+      }
+      float bs = score;
+      int bi = (lane < k) ? my_i : 0x7fffffff;
+      float bl = my_v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; bl = ol; }
+      }
+      if (lane == 0) {
+        const long long pred = static_cast<long long>(bi);
+        const float prob = __expf(bl - m_row) / s_row;           // softmax(logits)[pred], unfiltered, T = 1
+        if (p.pred_ids != nullptr) p.pred_ids[row] = pred;
+        bool is_mask = true;
+        if (p.ids != nullptr) {
+          is_mask = (p.ids[row] == p.mask_id);
+          if (is_mask) p.ids[row] = pred;
+        }
+        if (p.scores != nullptr) p.scores[row] = is_mask ? (1.0f - prob) : -1e5f;
+      }
+    }
+    __syncthreads();      // everyone is done with buf / lists before the next bulk copy overwrites them
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // re-mask: per image, the k highest scores get mask_id (ties: lower token index first).
 // rank_i = #{j : s_j > s_i  or (s_j == s_i and j < i)};  token i is re-masked iff rank_i < k.
 // ---------------------------------------------------------------------------------------------
@@ -539,7 +784,28 @@ int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
   if (p.logits == nullptr || p.M <= 0 || p.V <= 0 || (p.V & 3) != 0 || (p.ld & 3) != 0) return PM_ERR_INVALID;
   if (p.topk < 1 || p.topk > 32 || p.topk > p.V) return PM_ERR_INVALID;
   const int row_bytes = p.V * 4;
-  if ((p.V % 128) == 0 && row_bytes <= 65536 && (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {
+  static int variant = -1;                       // PM_MASKGIT_VARIANT: 0 = auto, 1 = warp-per-row staged kernel, 2 = streaming
+  if (variant < 0) {
+    const char* env = getenv("PM_MASKGIT_VARIANT");
+    variant = env != nullptr ? atoi(env) : 0;
+  }
+  if (variant == 0 && (p.V % 2048) == 0 && row_bytes <= 65536 && (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {
+    // block-per-row staged kernel: 4 warps per row buffer, as many blocks per SM as fit (6 for V = 8192)
+    const int smem = row_bytes + 128 + MGB_WARPS * MGB_CAND * 8 + 256;
+    static bool attr_set_b = false;
+    if (!attr_set_b) {
+      cudaError_t e = cudaFuncSetAttribute(maskgit_sample_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4096);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_set_b = true;
+    }
+    int per_sm = (232448 - 1024) / (smem + 1024);
+    if (per_sm > 8) per_sm = 8;
+    int blocks = pm_num_sms() * per_sm;
+    if (blocks > p.M) blocks = p.M;
+    maskgit_sample_block_kernel<<<blocks, MGB_WARPS * 32, smem, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  if (variant != 2 && (p.V % 128) == 0 && row_bytes <= 65536 && (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {
     // shared-memory staged kernel: as many row buffers per SM as fit (6 x 32 KB for V = 8192)
     constexpr int W = 6;
     const int smem = W * row_bytes + 64 + W * MG_CAND * 8;

@@ -73,6 +73,19 @@ def pack_w3(w3, hp):
     return out.contiguous()
 
 
+def pos_operand(pos):
+    """How a GEMM adds a [N_tokens, D] position-embedding table (layers.py:108,146; transformer.py:82).  When the token
+    count is a multiple of the 128-row tile the table is handed over in bf16 as a row-periodic residual (`res_mod`):
+    it is then staged by TMA through the same shared-memory tile the result leaves from, instead of 16-byte fp32
+    loads scattered over 32 table rows per warp (measured: patch-embed 0.30 -> ms, post_quant 0.30 -> ms at
+    B = 256).  The sum is rounded to bf16 right afterwards, so the table's own bf16 rounding (|pos| * 2^-9) is far
+    below the result's.  Other token counts keep the fp32 path."""
+    pos = pos.float().contiguous()
+    if pos.shape[0] % 128 == 0:
+        return dict(res=pos.to(torch.bfloat16).contiguous(), res_mod=pos.shape[0])
+    return dict(pos=pos)
+
+
 class _Block:
     """Packed operands of one pre-LN transformer block (self-attention [+ cross-attention] + SwiGLU)."""
 
@@ -237,15 +250,23 @@ class Stage1Engine:
                     raise RuntimeError("paintmind_b200 patch kernels are built for patch_size = 8")
                 conv = enc.to_patch_embedding[0].weight.detach()
                 self.w_pe = conv.reshape(conv.shape[0], -1).to(torch.bfloat16).contiguous()       # [D, C*P*P], K order (c,kh,kw)
-                self.enc_pos = enc.position_embedding.detach()[0].float().contiguous()            # [N, D]
+                self.enc_pos = pos_operand(enc.position_embedding.detach()[0])                    # [N, D]
                 self.pre_g = enc.norm_pre.weight.detach().float().contiguous()
                 self.pre_b = enc.norm_pre.bias.detach().float().contiguous()
                 self.enc_blocks = [_Block(l, enc.num_head) for l in enc.transformer.layers]
             if dec is not None:
-                self.dec_pos = dec.position_embedding.detach()[0].float().contiguous()
+                self.dec_pos = pos_operand(dec.position_embedding.detach()[0])
+                self.dec_pos_f32 = dec.position_embedding.detach()[0].float().contiguous()
                 self.dec_blocks = [_Block(l, dec.num_head) for l in dec.transformer.layers]
                 self.w_proj, self.cs_proj, self.b_proj = fold_layernorm(dec.proj.weight.detach(), dec.proj.bias.detach(),
                                                                         dec.norm.weight.detach(), dec.norm.bias.detach())
+                # fp32 NCHW store (PM_OUT_UNPATCH) wants output columns in (c p1 p2) order instead of the reference's
+                # (p1 p2 c) (layers.py:150): permute the rows of proj once; the uint8 NHWC store keeps the original.
+                P, Cc = dec.patch_size, dec.out_channels
+                perm = torch.arange(P * P * Cc, device=self.w_proj.device).view(P, P, Cc).permute(2, 0, 1).reshape(-1)
+                self.w_proj_chw = self.w_proj[perm].contiguous()
+                self.cs_proj_chw = self.cs_proj[perm].contiguous()
+                self.b_proj_chw = self.b_proj[perm].contiguous()
             m = self.model
             if m is not None:
                 self.w_prev = m.prev_quant.weight.detach().to(torch.bfloat16).contiguous()        # [32, D]
@@ -290,7 +311,7 @@ class Stage1Engine:
             ops.patchify8_u8(img, patches)
         else:
             ops.patchify8(img, patches)
-        ops.gemm(patches, self.w_pe, x0, pos=self.enc_pos)                        # conv-as-GEMM + position embedding
+        ops.gemm(patches, self.w_pe, x0, **self.enc_pos)                        # conv-as-GEMM + position embedding
         ops.layernorm(x0, gamma=self.pre_g, beta=self.pre_b, y=x, stats=st.finished())   # norm_pre (+ stats of its output)
         run_blocks(self.enc_blocks, x, st, B, N, ws)
         return x.view(B, N, D)
@@ -326,12 +347,12 @@ class Stage1Engine:
         # decoder.norm folded into proj; un-patchify + clamp (+ `restore` to uint8 pixels) fused into the store
         if pixels:
             img = torch.empty(B, dec.image_size, dec.image_size, 3, device=dev, dtype=torch.uint8)
-            mode = PM_OUT_UNPATCH_U8
+            ops.gemm(x, self.w_proj, img, bias=self.b_proj, colsum=self.cs_proj,
+                     out_mode=PM_OUT_UNPATCH_U8, patch=8, channels=3, grid=g, **st.consume())
         else:
             img = torch.empty(B, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
-            mode = PM_OUT_UNPATCH
-        ops.gemm(x, self.w_proj, img, bias=self.b_proj, colsum=self.cs_proj,
-                 out_mode=mode, patch=8, channels=3, grid=g, **st.consume())
+            ops.gemm(x, self.w_proj_chw, img, bias=self.b_proj_chw, colsum=self.cs_proj_chw,
+                     out_mode=PM_OUT_UNPATCH, patch=8, channels=3, grid=g, **st.consume())
         return img
 
     def decode(self, z, pixels=False):
@@ -359,7 +380,7 @@ class Stage1Engine:
         M, D = B * N, dec.dim
         x = self.ws.get("x", (M, D), torch.bfloat16, dev)
         st = _RowStats(self.ws, M, D, dev)
-        ops.gemm(zs, self.w_post, x, bias=self.b_post, pos=self.dec_pos, stats_out=st.produce())   # post_quant + pos-emb
+        ops.gemm(zs, self.w_post, x, bias=self.b_post, stats_out=st.produce(), **self.dec_pos)   # post_quant + pos-emb
         return self._decode_tokens_inplace(x, st, B, N, dev, pixels)
 
     def decode_from_indice(self, indice, pixels=False):
@@ -387,7 +408,7 @@ class Stage1Engine:
         dev = tokens.device
         x = self.ws.get("x", (M, D), torch.bfloat16, dev)
         st = _RowStats(self.ws, M, D, dev)
-        x.copy_((tokens.detach().float() + self.dec_pos[None]).reshape(M, D))
+        x.copy_((tokens.detach().float() + self.dec_pos_f32[None]).reshape(M, D))
         ops.layernorm(x, stats=st.finished())
         return self._decode_tokens_inplace(x, st, B, N, dev)
 
@@ -420,7 +441,8 @@ class Stage2Engine:
             wt = tr.token_proj.weight.detach().float()
             self.w_tok = torch.cat([wt, wt], dim=1).to(torch.bfloat16).contiguous()          # against [hi | lo]
             self.b_tok = tr.token_proj.bias.detach().float().contiguous()
-            self.pos = tr.position_embedding.detach()[0].float().contiguous()
+            self.pos = pos_operand(tr.position_embedding.detach()[0])
+            self.n_tokens = tr.position_embedding.shape[1]
             self.w_ctx = None
             if isinstance(tr.context_proj, torch.nn.Linear):
                 self.w_ctx = tr.context_proj.weight.detach().to(torch.bfloat16).contiguous()
@@ -456,11 +478,11 @@ class Stage2Engine:
         tr = self.tr
         dev = zs.device
         M, D = B * N, tr.dim
-        if N != self.pos.shape[0]:
-            raise RuntimeError(f"expected {self.pos.shape[0]} tokens per sample, got {N}")
+        if N != self.n_tokens:
+            raise RuntimeError(f"expected {self.n_tokens} tokens per sample, got {N}")
         x = self.ws.get("x", (M, D), torch.bfloat16, dev)
         st = _RowStats(self.ws, M, D, dev)
-        ops.gemm(zs, self.w_tok, x, bias=self.b_tok, pos=self.pos, stats_out=st.produce())   # token_proj + pos-emb
+        ops.gemm(zs, self.w_tok, x, bias=self.b_tok, stats_out=st.produce(), **self.pos)   # token_proj + pos-emb
         kvs, L = None, 0
         if context is not None:
             kvs = self._context_kv(context)

@@ -73,7 +73,7 @@ def stats_parts(n, bn=None):
 
 def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, out_mode=PM_OUT_BF16,
          swiglu=False, bn=0, n=None, patch=0, channels=0, grid=0, max_ctas=0, stats_out=None, stats_raw=0,
-         ln_eps=1e-5, cta_group=0, debug=None):
+         ln_eps=1e-5, cta_group=0, debug=None, res_mod=0):
     """out = epilogue(a[M,K] @ w[N,K]^T); see pm_gemm_bf16 in include/paintmind_b200.h."""
     _require_cuda(a, w, out)
     args = _lib.GemmArgs()
@@ -91,6 +91,7 @@ def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, o
     args.stats_raw, args.ln_eps, args.stats_out = int(stats_raw), float(ln_eps), _ptr(stats_out)
     args.cta_group = int(cta_group)
     args.debug = _ptr(debug)
+    args.res_mod = int(res_mod)
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_gemm_bf16(C.byref(args), _stream()), "pm_gemm_bf16")
     _prof_end(t0, ("gemm", args.M, args.N, args.K, bool(swiglu), res is not None, stats is not None, out_mode))

@@ -159,7 +159,8 @@ def main():
     a, w = mk(M, N, K)
     bias = torch.randn(N, device=dev) * 0.1
     img = torch.full((B, Cc, G * P, G * P), float("nan"), device=dev)
-    run_gemm(a, w, img, bias=bias, out_mode=2, patch=P, channels=Cc, grid=G)
+    perm = torch.arange(N, device=dev).view(P, P, Cc).permute(2, 0, 1).reshape(-1)      # (p1 p2 c) -> (c p1 p2) rows
+    run_gemm(a, w[perm].contiguous(), img, bias=bias[perm].contiguous(), out_mode=2, patch=P, channels=Cc, grid=G)
     torch.cuda.synchronize()
     y = (a.float() @ w.float().t() + bias).reshape(B, G, G, P, P, Cc).permute(0, 5, 1, 3, 2, 4).reshape(B, Cc, G * P, G * P).clamp(-1, 1)
     all_ok &= report("unpatchify", img.reshape(-1, G * P), y.reshape(-1, G * P), 2e-3)

@@ -1,0 +1,91 @@
+"""Achieved HBM bandwidth of the memory-bound kernels of the path (CUDA events, inputs larger than L2 or an L2 flush
+between launches).  Prints one line per kernel: algorithmic bytes, time, GB/s, fraction of the measured copy peak."""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from paintmind_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+peak = 6457.4
+mp = ROOT / "MEASURED_PEAKS.json"
+if mp.exists():
+    peak = json.loads(mp.read_text())["hbm_gbs"]
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # 512 MB > 126 MB L2
+
+
+def timeit(fn, iters=10):
+    fn(); fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()                                                # evict L2
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+rows = []
+
+
+def report(name, nbytes, ms):
+    gbs = nbytes / ms / 1e6
+    rows.append({"kernel": name, "bytes": nbytes, "ms": ms, "gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+    print(f"{name:44s} {nbytes / 1e6:10.1f} MB {ms:8.3f} ms {gbs:8.0f} GB/s  {100 * gbs / peak:5.1f}% of {peak:.0f}")
+
+
+B, N, D, V = 256, 1024, 512, 8192
+M = B * N
+g = torch.Generator(device=dev).manual_seed(0)
+
+# layernorm (norm_pre): read x bf16, write y bf16 (+ 8 B/row stats)
+x = torch.randn(M, D, device=dev, generator=g).bfloat16()
+y = torch.empty_like(x)
+gam, bet = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+st = torch.empty(M, 2, device=dev)
+report("layernorm [262144,512] bf16 (norm_pre)", 2 * M * D * 2 + M * 8, timeit(lambda: ops.layernorm(x, gamma=gam, beta=bet, y=y, stats=st)))
+
+# patchify fp32 NCHW -> bf16 patches: 12 B/px in, 6 B/px out
+img = torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1
+patches = torch.empty(M, 192, device=dev, dtype=torch.bfloat16)
+report("patchify8 fp32 NCHW [256,3,256,256]", img.numel() * 4 + patches.numel() * 2, timeit(lambda: ops.patchify8(img, patches)))
+
+# patchify uint8 NHWC -> bf16 patches: 3 B/px in, 6 B/px out
+u8 = torch.randint(0, 256, (B, 256, 256, 3), device=dev, dtype=torch.uint8, generator=g)
+report("patchify8_u8 uint8 NHWC [256,256,256,3]", u8.numel() + patches.numel() * 2, timeit(lambda: ops.patchify8_u8(u8, patches)))
+
+# MaskGIT sampling tail and masked CE over fp32 logits [65536, 8192] (2.1 GB)
+Ms = 64 * N
+logits = torch.randn(Ms, V, device=dev, generator=g)
+ids = torch.full((Ms,), V, device=dev, dtype=torch.int64)
+pred = torch.empty(Ms, device=dev, dtype=torch.int64)
+sc = torch.empty(Ms, device=dev)
+report("maskgit_sample [65536,8192] fp32 topk5", Ms * V * 4 + Ms * 20,
+       timeit(lambda: ops.maskgit_sample(logits, topk=5, temperature=1.0, ids=ids, pred_ids=pred, scores=sc, mask_id=V, seed=1, offset=1), iters=5))
+label = torch.randint(0, V, (Ms,), device=dev, generator=g)
+row = torch.empty(Ms, device=dev)
+out = torch.empty((), device=dev)
+report("ce_label_smooth [65536,8192] all rows", Ms * V * 4 + Ms * 12,
+       timeit(lambda: ops.ce_label_smooth(logits, label, None, 0.1, row_loss=row, loss_out=out), iters=5))
+mask = (torch.rand(Ms, device=dev, generator=g) < 0.75).float()
+nm = int(mask.sum().item())
+report("ce_label_smooth [65536,8192] 75% masked rows", nm * V * 4 + Ms * 16,
+       timeit(lambda: ops.ce_label_smooth(logits, label, mask, 0.1, row_loss=row, loss_out=out), iters=5))
+
+# gathers: ids -> [hi|lo] token operand
+table = torch.randn(V + 1, 32, device=dev, generator=g)
+zs = torch.empty(Ms, 64, device=dev, dtype=torch.bfloat16)
+idl = torch.randint(0, V + 1, (Ms,), device=dev, generator=g)
+report("vq_gather ids->[hi|lo] [65536]", Ms * (8 + 128), timeit(lambda: ops.vq_gather(idl, table, False, None, zs)))
+z = torch.randn(M, 32, device=dev, generator=g)
+zs2 = torch.empty(M, 64, device=dev, dtype=torch.bfloat16)
+report("split_rows32 [262144,32] fp32->[hi|lo]", M * (128 + 128), timeit(lambda: ops.split_rows32(z, zs2)))
+
+(ROOT / "gpurun_out").mkdir(exist_ok=True)
+(ROOT / "gpurun_out" / "membound.json").write_text(json.dumps(rows, indent=1))

@@ -37,7 +37,7 @@ def test_library_builds_loads_and_exports_all_declared_symbols():
 def test_struct_layouts_match_header_sizes():
     """ctypes mirrors of the argument structs: natural alignment, pointer/int64 fields first then int32."""
     from paintmind_b200 import _lib
-    assert ctypes.sizeof(_lib.GemmArgs) == 8 * 8 + 5 * 8 + 12 * 4 + 4 + 4 + 8 + 8 + 8  # 8 ptrs, 5 i64, 12 i32, f32, pad, ptr, i32+pad, ptr
+    assert ctypes.sizeof(_lib.GemmArgs) == 8 * 8 + 5 * 8 + 12 * 4 + 4 + 4 + 8 + 8 + 8 + 8  # 8 ptrs, 5 i64, 12 i32, f32, pad, ptr, i32+pad, ptr, i32+pad
     assert ctypes.sizeof(_lib.AttnArgs) == 4 * 8 + 8 * 8 + 5 * 4 + 4
     assert ctypes.sizeof(_lib.VqArgs) == 10 * 8 + 8 + 4 * 4
     assert ctypes.sizeof(_lib.MaskgitSampleArgs) == 5 * 8 + 3 * 8 + 2 * 8 + 3 * 4 + 4

@@ -127,3 +127,29 @@ def test_weight_update_repacks(cuda_device):
     model.load_state_dict(synthetic.make_vqgan_state_dict(cfg, seed=3))
     _, _, idx_c = model.encode(x)
     assert torch.equal(idx_a, idx_c) and not torch.equal(idx_a, idx_b)
+
+
+def test_gemm_row_periodic_residual_table(cuda_device):
+    """`res_mod`: the position-embedding table handed to the GEMM as a row-periodic bf16 residual (staged by TMA)
+    gives the same result as the fp32 `pos` path up to the table's bf16 rounding."""
+    from paintmind_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for M, N, K, T in [(1024, 512, 192, 256), (2048, 512, 64, 1024), (384, 256, 64, 128)]:
+        a = (torch.randn(M, K, generator=g) * 0.5).to(cuda_device).bfloat16()
+        w = (torch.randn(N, K, generator=g) * 0.1).to(cuda_device).bfloat16()
+        bias = (torch.randn(N, generator=g) * 0.1).to(cuda_device)
+        pos = (torch.randn(T, N, generator=g) * 0.02).to(cuda_device)
+        o1 = torch.empty(M, N, device=cuda_device, dtype=torch.bfloat16)
+        o2 = torch.empty_like(o1)
+        ops.gemm(a, w, o1, bias=bias, pos=pos)
+        ops.gemm(a, w, o2, bias=bias, res=pos.bfloat16().contiguous(), res_mod=T)
+        ref = a.float() @ w.float().t() + bias + pos.bfloat16().float().repeat(M // T, 1)
+        assert (o2.float() - ref).abs().max() < 0.02 * max(1.0, ref.abs().max().item())
+        assert (o1.float() - o2.float()).abs().max() < 0.02
+        # statistics of the output rows still come out right on this path
+        st = torch.empty(M, ops.stats_parts(N), 2, device=cuda_device)
+        ops.gemm(a, w, o2, bias=bias, res=pos.bfloat16().contiguous(), res_mod=T, stats_out=st)
+        # (the statistics are taken before the bf16 rounding of the stored values: N roundings of ~2^-9 |x| apart)
+        torch.testing.assert_close(st[..., 0].sum(1), o2.float().sum(1), atol=0.3, rtol=1e-2)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w, o2, res=pos.bfloat16().contiguous(), res_mod=100)       # not a multiple of the 128-row tile

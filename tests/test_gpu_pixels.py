@@ -99,3 +99,25 @@ def test_encode_pixels_type_errors(cuda_device):
         model.encode_pixels(torch.zeros(1, S, S, 3, device=cuda_device))
     with pytest.raises(RuntimeError):
         model.encode_pixels(torch.zeros(1, S, S + 8, 3, device=cuda_device, dtype=torch.uint8))
+
+
+def test_unpatchify_store_modes_agree_with_einops_layout(cuda_device):
+    """The two fused stores of the last projection against the reference's rearrange
+    'b (h w) (p1 p2 c) -> b c (h p1) (w p2)' (layers.py:150) on a plain GEMM: fp32 NCHW (rows of W permuted to
+    (c p1 p2), see PM_OUT_UNPATCH) and uint8 NHWC (reference row order)."""
+    from paintmind_b200.ops import PM_OUT_F32, PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8
+    B, G, P, C, K = 2, 5, 8, 3, 128
+    g = torch.Generator().manual_seed(9)
+    a = (torch.randn(B * G * G, K, generator=g) * 0.2).to(cuda_device).bfloat16()
+    w = (torch.randn(P * P * C, K, generator=g) * 0.3).to(cuda_device).bfloat16()
+    bias = (torch.randn(P * P * C, generator=g) * 0.2).to(cuda_device)
+    flat = torch.empty(B * G * G, P * P * C, device=cuda_device)
+    ops.gemm(a, w, flat, bias=bias, out_mode=PM_OUT_F32)
+    want = flat.view(B, G, G, P, P, C).permute(0, 5, 1, 3, 2, 4).reshape(B, C, G * P, G * P).clamp(-1, 1)
+    perm = torch.arange(P * P * C, device=cuda_device).view(P, P, C).permute(2, 0, 1).reshape(-1)
+    img = torch.full((B, C, G * P, G * P), float("nan"), device=cuda_device)
+    ops.gemm(a, w[perm].contiguous(), img, bias=bias[perm].contiguous(), out_mode=PM_OUT_UNPATCH, patch=P, channels=C, grid=G)
+    assert torch.equal(img, want)
+    px = torch.zeros(B, G * P, G * P, C, device=cuda_device, dtype=torch.uint8)
+    ops.gemm(a, w, px, bias=bias, out_mode=PM_OUT_UNPATCH_U8, patch=P, channels=C, grid=G)
+    np.testing.assert_array_equal(px.cpu().numpy(), _reference_restore(want))

@@ -174,3 +174,62 @@ def test_pipeline_generate_runs_schedule(cuda_device, full_pipeline):
     imgs = pipe.generate(["a", "b"], timesteps=3, temperature=1.0, topk=5, save_interval=2)
     assert len(imgs) == 2 and all(i.device.type == "cpu" and tuple(i.shape) == (2, 3, 256, 256) for i in imgs)
     assert all(float(i.min()) >= -1 and float(i.max()) <= 1 for i in imgs)
+
+
+def _run_sample(logits2d, u2d, topk, temp, V):
+    from paintmind_b200 import ops
+    M = logits2d.shape[0]
+    pred = torch.empty(M, device=logits2d.device, dtype=torch.int64)
+    scores = torch.empty(M, device=logits2d.device)
+    ops.maskgit_sample(logits2d, topk=topk, temperature=temp, ids=None, pred_ids=pred, scores=scores, mask_id=V, noise=u2d)
+    return pred, scores
+
+
+@pytest.mark.parametrize("V", [8192, 2048])
+def test_maskgit_sample_degenerate_rows(cuda_device, V):
+    """Rows that overflow the candidate lists of the staged kernels (thousands of equal values): the result must
+    still be the reference's — top-k keeps the LOWEST indices among equal values (ties -> lower index), which is
+    what torch.topk's documented behaviour is not, so the comparison is against an explicit stable sort."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(77)
+    M, topk, temp = 9, 5, 0.8
+    logits = torch.randn(M, V, generator=g)
+    logits[0] = 1.25                                          # constant row
+    logits[1, : V // 2] = 3.0                                 # half the row tied at the maximum
+    logits[2] = torch.randint(0, 3, (V,), generator=g).float()    # three distinct values
+    logits[3, 100:400] = logits[3].max() + 1.0                # 300 equal maxima in one stretch
+    logits[4] = -1e30
+    logits[4, 7] = 0.0                                        # one finite-ish spike, everything else hugely negative
+    u = torch.rand(M, V, generator=g)
+    logits, u = logits.to(dev), u.to(dev)
+    pred, scores = _run_sample(logits, u, topk, temp, V)
+    # reference with the explicit tie rule: stable descending sort -> first k
+    order = torch.sort(logits, dim=-1, descending=True, stable=True).indices[:, :topk]
+    val = logits.gather(1, order)
+    lg = lambda t: torch.log(t.clamp(min=1e-20))  # noqa: E731
+    pert = val / max(temp, 1e-10) + (-lg(-lg(u.gather(1, order))))
+    # arg-max over the k survivors; ties -> lower vocabulary index
+    best = pert.max(dim=1, keepdim=True).values
+    cand = torch.where(pert == best, order, torch.full_like(order, V))
+    want = cand.min(dim=1).values
+    assert torch.equal(pred, want)
+    probs = logits.softmax(-1).gather(1, want[:, None])[:, 0]
+    torch.testing.assert_close(scores, 1 - probs, atol=2e-6, rtol=0)
+
+
+def test_maskgit_sample_kernel_variants_agree(cuda_device):
+    """The three sampling kernels (block-per-row staged, warp-per-row staged, streaming) are selected by shape; run
+    shapes that reach each of them on the same rows (padding the vocabulary with -inf) and compare."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    M, V = 40, 2048
+    base = (torch.randn(M, V, generator=g) * 2).to(dev)
+    u = torch.rand(M, V, generator=g).to(dev)
+    pred_a, sc_a = _run_sample(base, u, 5, 1.0, V)                                   # V % 2048 == 0: block-per-row
+    pad = torch.full((M, 128), float("-inf"), device=dev)
+    pred_b, sc_b = _run_sample(torch.cat([base, pad], 1).contiguous(), torch.cat([u, pad.abs().clamp(max=0.5)], 1).contiguous(), 5, 1.0, V + 128)   # % 128: warp-per-row
+    pad4 = torch.full((M, 4), float("-inf"), device=dev)
+    pred_c, sc_c = _run_sample(torch.cat([base, pad4], 1).contiguous(), torch.cat([u, pad4.abs().clamp(max=0.5)], 1).contiguous(), 5, 1.0, V + 4)   # streaming
+    assert torch.equal(pred_a, pred_b) and torch.equal(pred_a, pred_c)
+    torch.testing.assert_close(sc_a, sc_b, atol=2e-6, rtol=0)
+    torch.testing.assert_close(sc_a, sc_c, atol=2e-6, rtol=0)
