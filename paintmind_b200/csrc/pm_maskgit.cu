@@ -352,6 +352,10 @@ maskgit_sample_smem_kernel(const MaskgitParams p) {
 //   order) -> warp 0 selects the exact top-k (value desc, index asc), applies the gumbel arg-max and writes.
 // If a candidate list overflows (rows with thousands of equal values) the block falls back to k rounds of a
 // block-wide arg-max over the staged row: results never depend on the capacity.
+// Measured on [65536, 8192] (scripts/sample_variants.py, L2 flushed): this kernel 0.598 ms (3.6 TB/s), warp-per-row
+// staged 0.707 ms, streaming insertion 1.80 ms; a register-resident variant (256 threads holding the row in
+// registers, next row prefetched under the selection) was tried and measured SLOWER (0.695 ms) — the per-row critical
+// path (shuffle-serial tau / top-k selection), not the staging, is what limits these kernels.
 // ---------------------------------------------------------------------------------------------
 constexpr int MGB_WARPS = 4;
 constexpr int MGB_CAND = 64;      // per warp
@@ -784,7 +788,7 @@ int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
   if (p.logits == nullptr || p.M <= 0 || p.V <= 0 || (p.V & 3) != 0 || (p.ld & 3) != 0) return PM_ERR_INVALID;
   if (p.topk < 1 || p.topk > 32 || p.topk > p.V) return PM_ERR_INVALID;
   const int row_bytes = p.V * 4;
-  static int variant = -1;                       // PM_MASKGIT_VARIANT: 0 = auto, 1 = warp-per-row staged kernel, 2 = streaming
+  static int variant = -1;       // PM_MASKGIT_VARIANT (tuning aid): 0 = auto (block-per-row staged), 1 = warp-per-row staged, 2 = streaming
   if (variant < 0) {
     const char* env = getenv("PM_MASKGIT_VARIANT");
     variant = env != nullptr ? atoi(env) : 0;

@@ -318,6 +318,12 @@ class Stage1Engine:
 
     def encode(self, img):
         m = self.model
+        if img.shape[0] == 0:
+            # empty batch: what the reference returns (empty tensors; the mean over zero elements is nan)
+            enc = self.encoder
+            n = (enc.image_size // enc.patch_size) ** 2
+            return (torch.empty(0, n, m.quantize.e_dim, device=img.device), torch.full((), float("nan"), device=img.device),
+                    torch.empty(0, n, dtype=torch.int64, device=img.device))
         x = self.run_encoder(img)
         B, N, D = x.shape
         M = B * N
@@ -366,6 +372,8 @@ class Stage1Engine:
         B, N, E = z.shape
         M, D = B * N, dec.dim
         dev = z.device
+        if B == 0:
+            return self._empty_image(dev, pixels)
         z2d = z.reshape(M, E)
         if z2d.dtype != torch.float32:
             z2d = z2d.float()
@@ -374,6 +382,12 @@ class Stage1Engine:
         zs = self.ws.get("zs", (M, 2 * E), torch.bfloat16, dev)
         ops.split_rows32(z2d, zs)
         return self._decode_split(zs, B, N, dev, pixels)
+
+    def _empty_image(self, dev, pixels):
+        dec = self.decoder
+        if pixels:
+            return torch.empty(0, dec.image_size, dec.image_size, dec.out_channels, device=dev, dtype=torch.uint8)
+        return torch.empty(0, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
 
     def _decode_split(self, zs, B, N, dev, pixels=False):
         dec = self.decoder
@@ -392,6 +406,8 @@ class Stage1Engine:
         B, N = indice.shape
         M = B * N
         dev = indice.device
+        if B == 0:
+            return self._empty_image(dev, pixels)
         E = m.quantize.embedding.weight.detach().float().contiguous()
         zs = self.ws.get("zs", (M, 2 * m.quantize.e_dim), torch.bfloat16, dev)
         ops.vq_gather(indice.reshape(-1).to(torch.int64).contiguous(), E, True, None, zs)

@@ -51,6 +51,9 @@ class VectorQuantizer(nn.Module):
     def forward(self, z):
         self._check(z)
         shape = z.shape
+        if z.numel() == 0:       # empty input: empty outputs and the reference's nan (mean over zero elements)
+            return (torch.empty(shape, device=z.device), torch.full((), float("nan"), device=z.device),
+                    torch.empty(shape[:-1], dtype=torch.int64, device=z.device))
         z2d = z.detach().reshape(-1, self.e_dim)
         if z2d.dtype != torch.float32:
             z2d = z2d.float()
@@ -64,6 +67,8 @@ class VectorQuantizer(nn.Module):
     @torch.no_grad()
     def decode_from_indice(self, indices):
         self._check(indices)
+        if indices.numel() == 0:
+            return torch.empty(*indices.shape, self.e_dim, device=indices.device)
         E = self.embedding.weight.detach().float().contiguous()
         idx = indices.reshape(-1).to(torch.int64).contiguous()
         out = torch.empty(idx.numel(), self.e_dim, device=idx.device, dtype=torch.float32)

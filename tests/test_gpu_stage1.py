@@ -131,3 +131,19 @@ def test_vq_edge_cases(cuda_device):
         assert torch.all(gap[mism] < 1e-5), (M, n_e)
         if n_e >= 130:
             assert idx[0].item() == 3
+
+
+def test_empty_batch_matches_reference_conventions(cuda_device):
+    """B = 0: the reference returns empty tensors and a nan loss (mean over zero elements); so do we (no kernel launch)."""
+    cfg, sd, _ = seeded_vqgan("vit-tiny-test", 7)
+    model = _model("vit-tiny-test", sd, cuda_device)
+    S = cfg["enc"]["image_size"]
+    n = (S // 8) ** 2
+    z_q, loss, idx = model.encode(torch.empty(0, 3, S, S, device=cuda_device))
+    assert z_q.shape == (0, n, 32) and idx.shape == (0, n) and idx.dtype == torch.int64 and torch.isnan(loss)
+    assert model.decode(z_q).shape == (0, 3, S, S)
+    assert model.decode_from_indice(idx).shape == (0, 3, S, S)
+    assert model.decode_pixels(z_q).shape == (0, S, S, 3)
+    zq2, l2, i2 = model.quantize(torch.empty(0, n, 32, device=cuda_device))
+    assert zq2.shape == (0, n, 32) and i2.shape == (0, n) and torch.isnan(l2)
+    assert model.quantize.decode_from_indice(i2).shape == (0, n, 32)
