@@ -34,6 +34,17 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t row, uin
   return static_cast<float>(c0 >> 8) * (1.0f / 16777216.0f);   // [0, 1) with 24 random bits, like torch's uniform_
 }
 
+// Warp-wide max of a float through ONE redux.sync on an order-preserving integer image of the value (instead of five
+// dependent shuffle + max levels): the selection loops below are latency chains, not throughput work.
+__device__ __forceinline__ int f32_ordered(float x) {
+  const int i = __float_as_int(x);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float warp_max_f32(float x) {
+  const int m = __reduce_max_sync(0xffffffffu, f32_ordered(x));
+  return __int_as_float(m ^ ((m >> 31) & 0x7fffffff));
+}
+
 template <int KMAX>
 struct TopList {
   float v[KMAX];
@@ -352,7 +363,8 @@ maskgit_sample_smem_kernel(const MaskgitParams p) {
 //   order) -> warp 0 selects the exact top-k (value desc, index asc), applies the gumbel arg-max and writes.
 // If a candidate list overflows (rows with thousands of equal values) the block falls back to k rounds of a
 // block-wide arg-max over the staged row: results never depend on the capacity.
-// Measured on [65536, 8192] (scripts/sample_variants.py, L2 flushed): this kernel 0.598 ms (3.6 TB/s), warp-per-row
+// Measured on [65536, 8192] (scripts/sample_variants.py, L2 flushed): this kernel 0.539 ms (4.0 TB/s; 0.598 ms before the
+// warp maxima went through redux.sync), warp-per-row
 // staged 0.707 ms, streaming insertion 1.80 ms; a register-resident variant (256 threads holding the row in
 // registers, next row prefetched under the selection) was tried and measured SLOWER (0.695 ms) — the per-row critical
 // path (shuffle-serial tau / top-k selection), not the staging, is what limits these kernels.
@@ -383,41 +395,49 @@ maskgit_sample_block_kernel(const MaskgitParams p) {
   const int nvec = p.V >> 2;                                         // multiple of 128
   const float4* b4 = reinterpret_cast<const float4*>(buf);
   uint32_t phase = 0;
+  auto fetch_row = [&](int r) {                                      // one bulk copy of a logit row: global -> shared
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(row_bytes));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(buf)), "l"(reinterpret_cast<uint64_t>(p.logits + static_cast<size_t>(r) * p.ld)),
+                 "r"(static_cast<uint32_t>(row_bytes)), "r"(smem_u32(bar))
+                 : "memory");
+  };
   for (int row = blockIdx.x; row < p.M; row += gridDim.x) {
-    if (threadIdx.x == 0) {
-      mbar_arrive_expect_tx(bar, static_cast<uint32_t>(row_bytes));
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_u32(buf)), "l"(reinterpret_cast<uint64_t>(p.logits + static_cast<size_t>(row) * p.ld)),
-                   "r"(static_cast<uint32_t>(row_bytes)), "r"(smem_u32(bar))
-                   : "memory");
-    }
+    if (threadIdx.x == 0) fetch_row(row);
     mbar_wait(bar, phase);
     phase ^= 1;
-    // ---- pass 1: per-thread two largest values ----
+    // ---- pass 1: per-thread two largest values (four independent max / min chains, merged at the end) ----
     float t0 = -INFINITY, t1 = -INFINITY;
-    for (int c = threadIdx.x; c < nvec; c += MGB_WARPS * 32 * 4) {
-      float4 q[4];
+    {
+      float u0[4], u1[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) q[u] = b4[c + MGB_WARPS * 32 * u];
+      for (int u = 0; u < 4; ++u) { u0[u] = -INFINITY; u1[u] = -INFINITY; }
+      for (int c = threadIdx.x; c < nvec; c += MGB_WARPS * 32 * 4) {
+        float4 q[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        for (int u = 0; u < 4; ++u) q[u] = b4[c + MGB_WARPS * 32 * u];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          t1 = fmaxf(t1, fminf(t0, e[t]));
-          t0 = fmaxf(t0, e[t]);
+        for (int u = 0; u < 4; ++u) {
+          const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            u1[u] = fmaxf(u1[u], fminf(u0[u], e[t]));
+            u0[u] = fmaxf(u0[u], e[t]);
+          }
         }
       }
-    }
-    float mw = t0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+      for (int u = 0; u < 4; ++u) {
+        t1 = fmaxf(t1, fminf(t0, u0[u]));
+        t0 = fmaxf(t0, u0[u]);
+        t1 = fmaxf(t1, fminf(t0, u1[u]));       // u1[u] <= u0[u] <= t0: only t1 can change
+      }
+    }
+    const float mw = warp_max_f32(t0);
     // k-th largest of this warp's 64 leaders: a lower bound of the row's k-th largest value
     float a0 = t0, a1 = t1, tau_w = -INFINITY;
     for (int r = 0; r < k; ++r) {
-      float bv = a0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) bv = fmaxf(bv, __shfl_xor_sync(0xffffffffu, bv, o));
+      const float bv = warp_max_f32(a0);
       tau_w = bv;
       const unsigned who = __ballot_sync(0xffffffffu, a0 == bv);
       if (lane == __ffs(who) - 1) { a0 = a1; a1 = -INFINITY; }
@@ -539,16 +559,12 @@ maskgit_sample_block_kernel(const MaskgitParams p) {
 #pragma unroll
           for (int u = 0; u < 2 * MGB_WARPS; ++u)
             if (cv[u] > bv || (cv[u] == bv && ci[u] < bi)) { bv = cv[u]; bi = ci[u]; }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-          }
+          const float wv = warp_max_f32(bv);                                           // best value of the warp ...
+          const int wi = __reduce_min_sync(0xffffffffu, bv == wv ? bi : 0x7fffffff);      // ... at its lowest index
 #pragma unroll
           for (int u = 0; u < 2 * MGB_WARPS; ++u)
-            if (ci[u] == bi) { cv[u] = -INFINITY; ci[u] = 0x7fffffff; }
-          if (lane == r) { my_v = bv; my_i = bi; }
+            if (ci[u] == wi) { cv[u] = -INFINITY; ci[u] = 0x7fffffff; }
+          if (lane == r) { my_v = wv; my_i = wi; }
         }
       } else if (lane < k) {
         my_v = sel_v[lane];
@@ -564,16 +580,10 @@ maskgit_sample_block_kernel(const MaskgitParams p) {
         const float g = -logf(fmaxf(inner, 1e-20f));
         score = my_v / fmaxf(p.temperature, 1e-10f) + g;
       }
-      float bs = score;
-      int bi = (lane < k) ? my_i : 0x7fffffff;
-      float bl = my_v;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
-        if (os > bs || (os == bs && oi < bi)) { bs = os; bi = oi; bl = ol; }
-      }
+      const float bs = warp_max_f32(score);                                            // best perturbed score ...
+      const int bi = __reduce_min_sync(0xffffffffu, (lane < k && score == bs) ? my_i : 0x7fffffff);   // ... ties -> lower index
+      const unsigned owner = __ballot_sync(0xffffffffu, lane < k && my_i == bi);
+      const float bl = __shfl_sync(0xffffffffu, my_v, owner != 0 ? __ffs(owner) - 1 : 0);             // its logit
       if (lane == 0) {
         const long long pred = static_cast<long long>(bi);
         const float prob = __expf(bl - m_row) / s_row;           // softmax(logits)[pred], unfiltered, T = 1
@@ -586,7 +596,9 @@ maskgit_sample_block_kernel(const MaskgitParams p) {
         if (p.scores != nullptr) p.scores[row] = is_mask ? (1.0f - prob) : -1e5f;
       }
     }
-    __syncthreads();      // everyone is done with buf / lists before the next bulk copy overwrites them
+    // everyone is done with buf / lists before the next bulk copy overwrites them.  (Issuing the next row's copy
+    // before the selection and dropping this sync was measured: 0.68 ms instead of 0.54 — slower.)
+    __syncthreads();
   }
 }
 

@@ -8,7 +8,7 @@ cat gpurun_out/${TAG}_pytest_gpu.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 if [ "${2:-full}" = "full" ]; then
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 270 --csv --log-file gpurun_out/${TAG}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-maskgit > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bench.log
 # 4th gemm launch of a step = layer-0 w12 (SwiGLU epilogue); 2nd = qkv (LN fold)
@@ -20,5 +20,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn
     python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_attn.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:vq_main_kernel -s 1 -c 1 -o gpurun_out/${TAG}_vq -f \
     python scripts/bench_e2e_quick.py 256 > gpurun_out/${TAG}_ncu_vq.log 2>&1
+# memory-bound kernels: one capture each (DRAM bytes and throughput) out of the bandwidth micro-benchmark
+for kn in ce_rows_kernel maskgit_sample_block_kernel layernorm_kernel patchify8_u8_kernel; do
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s 2 -c 1 -o gpurun_out/${TAG}_$kn -f \
+    python scripts/membound_bench.py > gpurun_out/${TAG}_ncu_$kn.log 2>&1
+done
 fi
 ls -la gpurun_out/
