@@ -189,9 +189,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (the image default): keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to STDOUT: send its log to stderr so that stdout
+        # carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend="nccl", device_id=dev)
 
     cfg = ver2cfg["vit-s-vqgan"]

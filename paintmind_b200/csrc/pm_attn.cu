@@ -480,10 +480,10 @@ int pm_attn_launch(const AttnParams& p, cudaStream_t stream) {
         if (c.emu == e && c.split == s && c.defer == d && c.chain == ch && c.ping == pg) v = &c;
       if (v == nullptr) return PM_ERR_INVALID;
     }
-    const cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e != cudaSuccess) return static_cast<int>(e);
     fn = v->fn;
   }
+  static bool attr_done[PM_MAX_DEVICES] = {};
+  if ((rc = pm_ensure_dyn_smem(fn, AT_SMEM_BYTES, attr_done)) != 0) return rc;
   const long long items = static_cast<long long>((p.Nq + 2 * AT_BM - 1) / (2 * AT_BM)) * p.H * p.B;
   const int grid = items < pm_num_sms() ? static_cast<int>(items) : pm_num_sms();
   fn<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);

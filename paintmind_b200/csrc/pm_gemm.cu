@@ -70,6 +70,23 @@ __device__ __forceinline__ float silu_f(float x) {
   return x * r;
 }
 
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2): one issue slot per two elements.  The epilogues are issue-bound CUDA-core
+// code racing the tensor pipe (at K = 512 a 128 x 256 tile is ~4100 MMA cycles), so halving their instruction count is
+// what keeps the narrow-K projections (to_out, w12) from waiting on the epilogue.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2u(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+// silu(a) * b for two elements: the two MUFU ops per element stay scalar, everything around them is packed
+__device__ __forceinline__ float2 silu_mul2(float2 a, float2 b) {
+  const float2 t = __fmul2_rn(a, f2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+  const float2 d = __fadd2_rn(e, f2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(__fmul2_rn(a, r), b);
+}
+
 template <int BN, int OUT_MODE, bool SWIGLU, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -301,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if (tile + tile_stride < total_tiles) prefetch_stats(tile + tile_stride);
-      float row_s1 = 0.0f, row_s2 = 0.0f;   // statistics of this thread's output columns (for the next LayerNorm)
+      float2 row_s1 = f2(0.0f, 0.0f), row_s2 = f2(0.0f, 0.0f);   // statistics of this thread's output columns (even | odd), for the next LayerNorm
       const float nrmu = -rstd * mu;        // LN fold: rstd * (acc - mu * colsum) + bias == acc * rstd + (nrmu * colsum + bias)
       const float* pos_row = nullptr;
       if (p.pos != nullptr && row_ok) pos_row = p.pos + static_cast<size_t>(row % p.pos_rows) * p.ld_pos;
@@ -334,7 +351,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
           const int oc = c * 64 + h * 32;                   // output column inside the tile
-          float v[32];
+          float2 v2[16];                                   // the 32 output values of this thread, as 16 packed pairs
+          float* const v = reinterpret_cast<float*>(v2);
+          const float2 rstd2 = f2(rstd, rstd), nrmu2 = f2(nrmu, nrmu);
           if (SWIGLU) {
             uint32_t rg[32], rv[32];
             tmem_ld_x32(tacc + oc, rg);
@@ -346,27 +365,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float4 cg = *reinterpret_cast<const float4*>(&colvec[BN + oc + j]);
               const float4 bv = *reinterpret_cast<const float4*>(&colvec[BN / 2 + oc + j]);
               const float4 cv = *reinterpret_cast<const float4*>(&colvec[BN + BN / 2 + oc + j]);
-              const float bgs[4] = {bg.x, bg.y, bg.z, bg.w}, cgs[4] = {cg.x, cg.y, cg.z, cg.w};
-              const float bvs[4] = {bv.x, bv.y, bv.z, bv.w}, cvs[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float a = fmaf(__uint_as_float(rg[j + t]), rstd, fmaf(nrmu, cgs[t], bgs[t]));
-                const float b = fmaf(__uint_as_float(rv[j + t]), rstd, fmaf(nrmu, cvs[t], bvs[t]));
-                v[j + t] = silu_f(a) * b;
-              }
+              // LN fold: acc * rstd + (nrmu * colsum + bias), gate and value columns
+              const float2 a0 = __ffma2_rn(f2u(rg[j], rg[j + 1]), rstd2, __ffma2_rn(nrmu2, f2(cg.x, cg.y), f2(bg.x, bg.y)));
+              const float2 a1 = __ffma2_rn(f2u(rg[j + 2], rg[j + 3]), rstd2, __ffma2_rn(nrmu2, f2(cg.z, cg.w), f2(bg.z, bg.w)));
+              const float2 b0 = __ffma2_rn(f2u(rv[j], rv[j + 1]), rstd2, __ffma2_rn(nrmu2, f2(cv.x, cv.y), f2(bv.x, bv.y)));
+              const float2 b1 = __ffma2_rn(f2u(rv[j + 2], rv[j + 3]), rstd2, __ffma2_rn(nrmu2, f2(cv.z, cv.w), f2(bv.z, bv.w)));
+              v2[j >> 1] = silu_mul2(a0, b0);
+              v2[(j >> 1) + 1] = silu_mul2(a1, b1);
             }
           } else {
             uint32_t ra[32];
             tmem_ld_x32(tacc + oc, ra);
             tmem_ld_wait();
+            if (p.stats != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(&colvec[oc + j]);
-              const float4 cc = *reinterpret_cast<const float4*>(&colvec[BN + oc + j]);
-              const float bbs[4] = {bb.x, bb.y, bb.z, bb.w}, ccs[4] = {cc.x, cc.y, cc.z, cc.w};
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(&colvec[oc + j]);
+                const float4 cc = *reinterpret_cast<const float4*>(&colvec[BN + oc + j]);
+                v2[j >> 1] = __ffma2_rn(f2u(ra[j], ra[j + 1]), rstd2, __ffma2_rn(nrmu2, f2(cc.x, cc.y), f2(bb.x, bb.y)));
+                v2[(j >> 1) + 1] = __ffma2_rn(f2u(ra[j + 2], ra[j + 3]), rstd2, __ffma2_rn(nrmu2, f2(cc.z, cc.w), f2(bb.z, bb.w)));
+              }
+            } else {
+              // no LayerNorm to fold (rstd = 1, mu = 0): acc + bias
 #pragma unroll
-              for (int t = 0; t < 4; ++t)
-                v[j + t] = fmaf(__uint_as_float(ra[j + t]), rstd, fmaf(nrmu, ccs[t], bbs[t]));
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(&colvec[oc + j]);
+                v2[j >> 1] = __fadd2_rn(f2u(ra[j], ra[j + 1]), f2(bb.x, bb.y));
+                v2[(j >> 1) + 1] = __fadd2_rn(f2u(ra[j + 2], ra[j + 3]), f2(bb.z, bb.w));
+              }
             }
             if (pos_row != nullptr) {
               const int col0 = tc.n0 + oc;
@@ -393,26 +419,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (has_res && h == 0) mbar_wait(&res_bar[grp * NSTG_G + gl % NSTG_G], (gl / NSTG_G) & 1);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float* x = &v[j * 8];
+              float2* x2 = &v2[j * 4];
               uint4* slot = reinterpret_cast<uint4*>(stg + (((h * 4 + j) ^ (row_in_tile & 7)) << 4));
               if (has_res) {
                 const uint4 r = *slot;
-                x[0] += bf16lo_to_f32(r.x); x[1] += bf16hi_to_f32(r.x);
-                x[2] += bf16lo_to_f32(r.y); x[3] += bf16hi_to_f32(r.y);
-                x[4] += bf16lo_to_f32(r.z); x[5] += bf16hi_to_f32(r.z);
-                x[6] += bf16lo_to_f32(r.w); x[7] += bf16hi_to_f32(r.w);
+                x2[0] = __fadd2_rn(x2[0], f2(bf16lo_to_f32(r.x), bf16hi_to_f32(r.x)));
+                x2[1] = __fadd2_rn(x2[1], f2(bf16lo_to_f32(r.y), bf16hi_to_f32(r.y)));
+                x2[2] = __fadd2_rn(x2[2], f2(bf16lo_to_f32(r.z), bf16hi_to_f32(r.z)));
+                x2[3] = __fadd2_rn(x2[3], f2(bf16lo_to_f32(r.w), bf16hi_to_f32(r.w)));
               }
               uint4 o;
-              o.x = pack_bf16x2(x[0], x[1]);
-              o.y = pack_bf16x2(x[2], x[3]);
-              o.z = pack_bf16x2(x[4], x[5]);
-              o.w = pack_bf16x2(x[6], x[7]);
+              o.x = pack_bf16x2(x2[0].x, x2[0].y);
+              o.y = pack_bf16x2(x2[1].x, x2[1].y);
+              o.z = pack_bf16x2(x2[2].x, x2[2].y);
+              o.w = pack_bf16x2(x2[3].x, x2[3].y);
               *slot = o;
               if (!SWIGLU && p.stats_out != nullptr) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  row_s1 += x[e];
-                  row_s2 = fmaf(x[e], x[e], row_s2);
+                for (int e = 0; e < 4; ++e) {
+                  row_s1 = __fadd2_rn(row_s1, x2[e]);
+                  row_s2 = __ffma2_rn(x2[e], x2[e], row_s2);
                 }
               }
             }
@@ -502,7 +528,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (OUT_MODE == OUT_BF16 && !SWIGLU && p.stats_out != nullptr && row_ok) {
         // slot (n_tile, group) of this row: [M, 2 * n_tiles, 2] — no atomics, no zero-fill, fixed summation order
         const int slot = (tile % n_tiles) * 2 + grp;
-        *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(row) * (2 * n_tiles) + slot) * 2) = make_float2(row_s1, row_s2);
+        *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(row) * (2 * n_tiles) + slot) * 2) = make_float2(row_s1.x + row_s1.y, row_s2.x + row_s2.y);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -558,12 +584,8 @@ static int launch_gemm(const GemmParams& p_in, cudaStream_t stream) {
     tmRes = tmA;
   }
   auto kern = gemm_kernel<BN, OUT_MODE, SWIGLU, CTA2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_done[PM_MAX_DEVICES] = {};
+  if ((rc = pm_ensure_dyn_smem(kern, Cfg::SMEM_BYTES, attr_done)) != 0) return rc;
   constexpr int TILE_M = CTA2 ? 2 * BM : BM;
   const int m_tiles = (p.M + TILE_M - 1) / TILE_M, n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;

@@ -74,6 +74,23 @@ struct MaskgitParams {
 };
 
 int pm_num_sms();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device).  `done` is a
+// call-site-owned `static bool[PM_MAX_DEVICES]` (zero-initialised).
+constexpr int PM_MAX_DEVICES = 64;
+template <typename Kern>
+inline int pm_ensure_dyn_smem(Kern kern, int bytes, bool* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (dev < 0 || dev >= PM_MAX_DEVICES) dev = PM_MAX_DEVICES - 1, done[dev] = false;
+  if (!done[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    done[dev] = true;
+  }
+  return 0;
+}
 int pm_cast_launch(const float* src, void* dst, long long n, cudaStream_t stream);
 int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream);
 int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, cudaStream_t stream);

@@ -808,12 +808,8 @@ int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
   if (variant == 0 && (p.V % 2048) == 0 && row_bytes <= 65536 && (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0) {
     // block-per-row staged kernel: 4 warps per row buffer, as many blocks per SM as fit (6 for V = 8192)
     const int smem = row_bytes + 128 + MGB_WARPS * MGB_CAND * 8 + 256;
-    static bool attr_set_b = false;
-    if (!attr_set_b) {
-      cudaError_t e = cudaFuncSetAttribute(maskgit_sample_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4096);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      attr_set_b = true;
-    }
+    static bool attr_done_b[PM_MAX_DEVICES] = {};
+    if (const int rc = pm_ensure_dyn_smem(maskgit_sample_block_kernel, 65536 + 4096, attr_done_b)) return rc;
     int per_sm = (232448 - 1024) / (smem + 1024);
     if (per_sm > 8) per_sm = 8;
     int blocks = pm_num_sms() * per_sm;
@@ -826,12 +822,8 @@ int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
     constexpr int W = 6;
     const int smem = W * row_bytes + 64 + W * MG_CAND * 8;
     if (smem <= 232448 - 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(maskgit_sample_smem_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        attr_set = true;
-      }
+      static bool attr_done[PM_MAX_DEVICES] = {};
+      if (const int rc = pm_ensure_dyn_smem(maskgit_sample_smem_kernel<W>, 232448 - 1024, attr_done)) return rc;
       const int per_sm = (232448 - 1024) / smem;                      // co-resident blocks when rows are short
       int blocks = pm_num_sms() * (per_sm > 4 ? 4 : per_sm);
       const int need = (p.M + W - 1) / W;

@@ -434,12 +434,8 @@ int pm_vq_launch(const VqParams& p_in, cudaStream_t stream) {
   CUtensorMap tmB;
   int rc = pm_make_tmap_2d(&tmB, p.packed, 2, p.n_e, 64, 64, VQ_BN, 64);
   if (rc != PM_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(vq_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VQ_SMEM_BYTES);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static bool attr_done[PM_MAX_DEVICES] = {};
+  if (const int rc = pm_ensure_dyn_smem(vq_main_kernel, VQ_SMEM_BYTES, attr_done)) return rc;
   const int items = ((p.M + VQ_BM - 1) / VQ_BM) * p.splits;
   const int grid = items < pm_num_sms() ? items : pm_num_sms();
   vq_main_kernel<<<grid, VQ_THREADS, VQ_SMEM_BYTES, stream>>>(tmB, p);

@@ -277,6 +277,7 @@ class Stage1Engine:
         self._fp = fp
 
     # -- encoder -------------------------------------------------------------------------------
+    @ops.on_device_of
     def run_encoder(self, img):
         """img fp32 NCHW in [-1, 1] -> tokens bf16 [B, N, D]  (Encoder.forward, layers.py:106-112).
         A uint8 [B, H, W, 3] tensor (decoded pixels) is also accepted: the reference's ingest transform
@@ -316,6 +317,7 @@ class Stage1Engine:
         run_blocks(self.enc_blocks, x, st, B, N, ws)
         return x.view(B, N, D)
 
+    @ops.on_device_of
     def encode(self, img):
         m = self.model
         if img.shape[0] == 0:
@@ -334,6 +336,7 @@ class Stage1Engine:
         loss = (r["sse"] * ((1.0 + m.quantize.beta) / (M * m.quantize.e_dim))).to(torch.float32).reshape(())
         return r["zq"].view(B, N, -1), loss, r["idx"].view(B, N)
 
+    @ops.on_device_of
     def latent(self, img):
         """encoder + prev_quant only (fp32 [B, N, 32]); used by parity tests."""
         m = self.model
@@ -361,6 +364,7 @@ class Stage1Engine:
                      out_mode=PM_OUT_UNPATCH, patch=8, channels=3, grid=g, **st.consume())
         return img
 
+    @ops.on_device_of
     def decode(self, z, pixels=False):
         """z [B, N, 32] -> image [B, 3, H, W] in [-1, 1]  (VQModel.decode, vqmodel.py:27-30);
         pixels=True -> uint8 [B, H, W, 3] = restore(decode(z)) (reconstruct.py:11-16)."""
@@ -397,6 +401,7 @@ class Stage1Engine:
         ops.gemm(zs, self.w_post, x, bias=self.b_post, stats_out=st.produce(), **self.dec_pos)   # post_quant + pos-emb
         return self._decode_tokens_inplace(x, st, B, N, dev, pixels)
 
+    @ops.on_device_of
     def decode_from_indice(self, indice, pixels=False):
         """ids [B, N] int64 -> image  (vqmodel.py:38-41, quantize.py:40-44)."""
         self._ensure_packed()
@@ -413,6 +418,7 @@ class Stage1Engine:
         ops.vq_gather(indice.reshape(-1).to(torch.int64).contiguous(), E, True, None, zs)
         return self._decode_split(zs, B, N, dev, pixels)
 
+    @ops.on_device_of
     def run_decoder_tokens(self, tokens):
         """Decoder.forward on [B, N, D] tokens (layers.py:145-152) -> un-clamped?  NOTE: the fused
         store clamps to [-1, 1] exactly like VQModel.decode; Decoder.forward alone is only reachable
@@ -508,6 +514,7 @@ class Stage2Engine:
         ops.gemm(x, self.w_logits, logits, bias=self.b_logits, colsum=self.cs_logits, out_mode=PM_OUT_F32, **st.consume())
         return logits.view(B, N, tr.num_classes)
 
+    @ops.on_device_of
     def forward(self, tokens, context=None):
         self._ensure_packed()
         if not tokens.is_cuda:
@@ -522,6 +529,7 @@ class Stage2Engine:
         ops.split_rows32(t2d, zs)
         return self._run(zs, B, N, context)
 
+    @ops.on_device_of
     def forward_from_ids(self, ids, table, context=None):
         """ids2tokens (generate.py:148-157) fused with the token split: ids -> [hi | lo] rows of the raw table."""
         self._ensure_packed()
@@ -544,6 +552,7 @@ def engine_for(module):
 # ------------------------------------------------------------------------------------------------
 # stand-alone module forwards (unit parity tests of rows a8 / a9)
 # ------------------------------------------------------------------------------------------------
+@ops.on_device_of
 def standalone_attention(mod, x, context=None):
     """CrossAttention.forward (attention.py:43-59) on the CUDA kernels; returns x.dtype."""
     if not x.is_cuda:
@@ -568,6 +577,7 @@ def standalone_attention(mod, x, context=None):
     return out.view(B, N, Dq).to(x.dtype)
 
 
+@ops.on_device_of
 def standalone_swiglu(mod, x):
     """SwiGLUFFN.forward (mlp.py:27-31) on the CUDA kernels; returns x.dtype."""
     if not x.is_cuda:

@@ -72,6 +72,7 @@ class Pipeline(nn.Module):
     # Forward values only: like every other entry point of this package the result carries no autograd graph
     # (the backward pass of the transformer is out of scope).
     @torch.no_grad()
+    @ops.on_device_of
     def random_masking(self, x, mask_ratio, _noise=None):
         """generate.py:78-108 -> (x with masked rows replaced by mask_token, mask [N, L] fp32 with 1 = masked).
         `_noise` injects the [N, L] uniforms the reference draws with torch.rand (parity tests); production
@@ -103,6 +104,7 @@ class Pipeline(nn.Module):
         return out.view(N, L, D), mask
 
     @torch.no_grad()
+    @ops.on_device_of
     def loss(self, logit, label, masks):
         """generate.py:110-123: label-smoothed (0.1) cross entropy averaged over the masked positions."""
         if not logit.is_cuda:
@@ -162,6 +164,7 @@ class Pipeline(nn.Module):
         return self._table
 
     @torch.no_grad()
+    @ops.on_device_of
     def ids2tokens(self, ids):
         table = self._token_table()
         flat = ids.reshape(-1).to(torch.int64).contiguous()
@@ -170,6 +173,7 @@ class Pipeline(nn.Module):
         return out.reshape(*ids.shape, table.shape[1])
 
     @torch.no_grad()
+    @ops.on_device_of
     def sample(self, ids, mask_ratio, text=None, topk=1, temperature=1, decode=True, _noise=None):
         """One MaskGIT step (generate.py:159-181) -> (ids, img).  `decode=False` skips the per-step
         ViT decode (the reference decodes every step even when generate() discards the image, F9)."""

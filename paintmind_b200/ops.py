@@ -45,9 +45,32 @@ def _stream():
 
 
 def _require_cuda(*ts):
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("paintmind_b200 kernels need CUDA tensors (no CPU fallback)")
+        dev = t.device.index if dev is None else dev
+    if dev is not None and dev != torch.cuda.current_device():
+        raise RuntimeError(f"paintmind_b200: tensors live on cuda:{dev} but the current device is cuda:{torch.cuda.current_device()}; "
+                           "kernels launch on the current device's stream — wrap the call in `with torch.cuda.device(...)` "
+                           "(the module-level entry points do this themselves)")
+
+
+def on_device_of(fn):
+    """Decorator for entry points: run with the first tensor argument's device current, so that kernels, tensor maps
+    and per-device function attributes all refer to the device the data lives on (single-process multi-GPU use)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = next((a for a in args if torch.is_tensor(a)), None)
+        if t is None or not t.is_cuda or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def gemm_tile_n(n, out_mode=PM_OUT_BF16, swiglu=False):

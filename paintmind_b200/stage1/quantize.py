@@ -27,6 +27,7 @@ class VectorQuantizer(nn.Module):
             raise RuntimeError("paintmind_b200 VQ kernels are built for e_dim = 32")
 
     @torch.no_grad()
+    @ops.on_device_of
     def quantize_2d(self, z2d, want_split=False):
         """z2d: fp32 [M, 32] (row stride multiple of 4).  Returns dict(idx, zq, zq_split, sse, hist)."""
         self._check(z2d)
@@ -48,6 +49,7 @@ class VectorQuantizer(nn.Module):
         return dict(idx=idx, zq=zq, zq_split=zs, sse=sse, hist=hist)
 
     @torch.no_grad()
+    @ops.on_device_of
     def forward(self, z):
         self._check(z)
         shape = z.shape
@@ -65,6 +67,7 @@ class VectorQuantizer(nn.Module):
         return r["zq"].reshape(shape), loss, r["idx"].reshape(shape[:-1])
 
     @torch.no_grad()
+    @ops.on_device_of
     def decode_from_indice(self, indices):
         self._check(indices)
         if indices.numel() == 0:

@@ -13,6 +13,20 @@ from .layers import Decoder, Encoder
 from .quantize import VectorQuantizer
 
 
+def _as_autocast(img):
+    """Return-dtype convention of the reference under `torch.autocast('cuda', ...)` (its trainers call the model
+    inside one, utils/trainer.py:187): the last op of decode is an autocast Linear, so the image comes back in the
+    autocast dtype; z_q, loss (fp32) and indices (int64) do not change.  The kernels always compute
+    in bf16 with fp32 accumulation; this only matches the dtype the caller's code expects."""
+    try:
+        on = torch.is_autocast_enabled("cuda")
+        dt = torch.get_autocast_dtype("cuda") if on else None
+    except TypeError:                                       # older torch: no device_type argument
+        on = torch.is_autocast_enabled()
+        dt = torch.get_autocast_gpu_dtype() if on else None
+    return img.to(dt) if on and img.is_floating_point() else img
+
+
 class VQModel(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -37,7 +51,7 @@ class VQModel(nn.Module):
     @torch.no_grad()
     def decode(self, x):
         """[B,N,32] -> image [B,3,H,W] clamped to [-1,1] — vqmodel.py:27-30."""
-        return self.engine().decode(x)
+        return _as_autocast(self.engine().decode(x))
 
     @torch.no_grad()
     def forward(self, img):
@@ -46,7 +60,7 @@ class VQModel(nn.Module):
 
     @torch.no_grad()
     def decode_from_indice(self, indice):
-        return self.engine().decode_from_indice(indice)
+        return _as_autocast(self.engine().decode_from_indice(indice))
 
     def from_pretrained(self, path):
         return self.load_state_dict(torch.load(path))

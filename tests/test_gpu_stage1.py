@@ -147,3 +147,40 @@ def test_empty_batch_matches_reference_conventions(cuda_device):
     zq2, l2, i2 = model.quantize(torch.empty(0, n, 32, device=cuda_device))
     assert zq2.shape == (0, n, 32) and i2.shape == (0, n) and torch.isnan(l2)
     assert model.quantize.decode_from_indice(i2).shape == (0, n, 32)
+
+
+def test_second_device_in_one_process(cuda_device):
+    """Single-process multi-GPU use: a model living on cuda:1 while cuda:0 is current gives the same bits as on cuda:0
+    (entry points switch to the tensors' device; per-device kernel attributes are set on both)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from paintmind_b200 import ops
+    cfg, sd, _ = seeded_vqgan("vit-tiny-test", 7)
+    S = cfg["enc"]["image_size"]
+    x = synthetic.make_images(3, S, seed=5)
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        model = _model("vit-tiny-test", sd, dev)
+        assert torch.cuda.current_device() == 0
+        z, loss, idx = model.encode(x.to(dev))
+        rec = model.decode(z)
+        outs.append((z.cpu(), loss.cpu(), idx.cpu(), rec.cpu()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="current device"):
+        ops.cast_bf16(torch.zeros(8, device="cuda:1"), torch.zeros(8, device="cuda:1", dtype=torch.bfloat16))
+
+
+def test_return_dtypes_under_cuda_autocast(cuda_device):
+    """under autocast the reference returns rec in the autocast dtype, z_q / loss fp32, indices int64."""
+    cfg, sd, _ = seeded_vqgan("vit-tiny-test", 7)
+    model = _model("vit-tiny-test", sd, cuda_device)
+    x = synthetic.make_images(2, cfg["enc"]["image_size"], seed=3).to(cuda_device)
+    rec32, _ = model(x)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        z_q, loss, idx = model.encode(x)
+        rec = model.decode(z_q)
+    assert z_q.dtype == torch.float32 and loss.dtype == torch.float32 and idx.dtype == torch.int64
+    assert rec.dtype == torch.bfloat16 and rec32.dtype == torch.float32
+    assert torch.equal(rec, rec32.to(torch.bfloat16))
