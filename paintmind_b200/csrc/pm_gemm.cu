@@ -34,9 +34,12 @@ constexpr int GEMM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue w
 // CTA2 = true: two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 of 256 x BN x 16.  Each CTA stages its own
 // 128 rows of A and HALF of the W tile (BN/2 rows), which halves the W bytes every SM pulls through L2 and smem
 // (the 1-CTA kernel is bound by L2->SM bandwidth: 128x256 tiles need ~12 TB/s at 1 PFLOP/s).
-template <int BN, bool CTA2>
+template <int BN, bool CTA2, bool SWIGLU = false>
 struct GemmCfg {
-  static constexpr int NSTG_G = 2;            // epilogue staging buffers per epilogue warp group
+  // epilogue staging buffers per epilogue warp group.  The SwiGLU projection never carries a residual (which is
+  // prefetched into the staging buffer one chunk ahead and therefore needs two): one buffer per group there, and the
+  // 32 KB saved buy a sixth operand stage (the MMA issuer of w12 waits 13 % of its time for operands with five).
+  static constexpr int NSTG_G = SWIGLU ? 1 : 2;
   static constexpr int NSTG = 2 * NSTG_G;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN, CTA2>;
+  using Cfg = GemmCfg<BN, CTA2, SWIGLU>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NSTG = Cfg::NSTG;
   constexpr int NSTG_G = Cfg::NSTG_G;
@@ -562,7 +565,7 @@ int pm_num_sms() {
 
 template <int BN, int OUT_MODE, bool SWIGLU, bool CTA2>
 static int launch_gemm(const GemmParams& p_in, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTA2>;
+  using Cfg = GemmCfg<BN, CTA2, SWIGLU>;
   static_assert(Cfg::STAGES >= 2, "not enough shared memory for a pipeline");
   GemmParams p = p_in;
   CUtensorMap tmA, tmB, tmOut, tmRes;
