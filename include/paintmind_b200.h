@@ -109,6 +109,8 @@ typedef struct pm_attn_args {
   int64_t bsq, bsk, bsv, bso;
   int32_t B, H, Nq, Nk, head_dim; /* head_dim must be 64 */
   float scale;                     /* dim_head ** -0.5 (attention.py:31) */
+  float* lse;                      /* optional out [B, H, Nq] fp32: log2-sum-exp2 of the scaled score rows, kept by a
+                                      training forward for pm_attn_bwd; NULL for inference */
 } pm_attn_args;
 
 int pm_attn_fwd(const pm_attn_args* args, void* stream);
@@ -211,6 +213,66 @@ int pm_maskgit_random_mask(const float* z, int64_t ldz, const float* noise, uint
                            void* stream);
 int pm_ce_label_smooth(const float* logits, int64_t ld, int32_t M, int32_t V, const int64_t* label, const float* mask,
                        float label_smoothing, float* row_loss, float* loss_out, double* sums_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generator BACKWARD path.  The reference has no backward code of its own: VQGANTrainer
+ * (utils/trainer.py:205-225) calls accelerator.backward(loss) and torch autograd differentiates the modules of the
+ * forward path.  These entry points are what a torch.autograd.Function.backward of that path calls
+ * (paintmind_b200/train.py); every one of them cites the forward lines it differentiates.
+ *
+ *   dgrad (dX = dY W) of every nn.Linear is pm_gemm_bf16 itself with the transposed weight as `w`.
+ *   pm_wgrad_bf16       : dW[N, K] (+)= dY[M, N]^T X[M, K]  — nn.Linear / patch-conv weight gradients
+ *                         (attention.py:34-41, mlp.py:28-31, layers.py:82,129, vqmodel.py:13-14).  dY and X are read
+ *                         token-major in place (MN-major UMMA operands), the M dimension is split across CTAs and the
+ *                         partial tiles are summed in a fixed order.  lddy / ldx must cover N / K rounded up to 64
+ *                         columns.  work: pm_wgrad_workspace_floats(M, N, K) floats.
+ *   pm_colsum_bf16      : out[N] (+)= sum_m x[m, N] — bias gradients; position-embedding gradients when x is viewed
+ *                         as [B, tokens * D] (layers.py:108,146).  work: pm_colsum_workspace_floats(M, N) floats.
+ *   pm_layernorm_bwd    : nn.LayerNorm backward (layers.py:49,51,89,128): dx = LN'(x)^T (dn) (+ dres, the residual
+ *                         branch of layers.py:55-56), dgamma_dbeta[2, D] = (sum dn * xhat, sum dn).
+ *                         work: pm_layernorm_bwd_workspace_floats(M, D) floats.
+ *   pm_swiglu_bwd       : hidden = silu(x1) * x2 backward (mlp.py:29-30) on the tile-interleaved x12 the packed w12
+ *                         projection produces; also re-materialises `h` (operand of the w3 weight gradient).
+ *   pm_attn_bwd         : backward of softmax(scale Q K^T) V (attention.py:52-57): dq, dk, dv from q, k, v, o, d_o and
+ *                         the forward's lse.  delta: [B, H, Nq] fp32 scratch.  Nq, Nk multiples of 128 (self-attention
+ *                         of the tokenizer: 1024).
+ *   pm_vq_bwd           : VectorQuantizer backward (quantize.py:19,29-36): straight-through estimator + both loss
+ *                         terms; dz fp32 [M, 32], dz_split bf16 [M, 64] = [hi | lo], dE[n_e, 32] += (fp32 atomics).
+ *                         d_out: gradient of the returned z_q (may be NULL), d_loss: device scalar (may be NULL).
+ *   pm_unpatchify8_bwd  : backward of clamp(-1, 1) (vqmodel.py:30) + un-patchify (layers.py:150): d_img fp32 NCHW ->
+ *                         bf16 rows [B * tokens, C * 64] in (c p1 p2) order, zero where rec sits on a clamp bound.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pm_attn_bwd_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* o;      /* forward output */
+  const void* d_o;    /* gradient of o */
+  const float* lse;   /* [B, H, Nq] from pm_attn_fwd */
+  float* delta;       /* [B, H, Nq] scratch */
+  void* dq;
+  void* dk;
+  void* dv;
+  int64_t ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  int64_t bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv;
+  int32_t B, H, Nq, Nk, head_dim;
+  float scale;
+} pm_attn_bwd_args;
+
+int pm_attn_bwd(const pm_attn_bwd_args* args, void* stream);
+int64_t pm_wgrad_workspace_floats(int32_t M, int32_t N, int32_t K);
+int pm_wgrad_bf16(const void* dy, int64_t lddy, const void* x, int64_t ldx, int32_t M, int32_t N, int32_t K, float* work,
+                  float* out, int64_t ld_out, int32_t accumulate, void* stream);
+int64_t pm_colsum_workspace_floats(int32_t M, int32_t N);
+int pm_colsum_bf16(const void* x, int64_t ld, int32_t M, int32_t N, float* work, float* out, int32_t accumulate, void* stream);
+int64_t pm_layernorm_bwd_workspace_floats(int32_t M, int32_t D);
+int pm_layernorm_bwd(const void* dn, int64_t lddn, const void* x, int64_t ldx, const float* gamma, const void* dres, int64_t ldres,
+                     void* dx, int64_t lddx, int32_t M, int32_t D, float eps, float* work, float* dgamma_dbeta, void* stream);
+int pm_swiglu_bwd(const void* x12, int64_t ld12, const void* dh, int64_t lddh, void* h, int64_t ldh, void* d12, int64_t ldd12,
+                  int32_t M, int32_t hp, void* stream);
+int pm_vq_bwd(const float* z, int64_t ldz, const int64_t* idx, const float* E, int32_t e_dim, const float* d_out, int64_t ldd,
+              const float* d_loss, float beta, int32_t M, float* dz, void* dz_split, float* dE, void* stream);
+int pm_unpatchify8_bwd(const float* d_img, const float* rec, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,20 @@ class AttnArgs(C.Structure):
         ("bsq", C.c_int64), ("bsk", C.c_int64), ("bsv", C.c_int64), ("bso", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("head_dim", C.c_int32),
         ("scale", C.c_float),
+        ("lse", C.c_void_p),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("d_o", C.c_void_p),
+        ("lse", C.c_void_p), ("delta", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64), ("lddo", C.c_int64),
+        ("lddq", C.c_int64), ("lddk", C.c_int64), ("lddv", C.c_int64),
+        ("bsq", C.c_int64), ("bsk", C.c_int64), ("bsv", C.c_int64), ("bso", C.c_int64), ("bsdo", C.c_int64),
+        ("bsdq", C.c_int64), ("bsdk", C.c_int64), ("bsdv", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float),
     ]
 
 
@@ -78,6 +92,12 @@ def load():
     lib.pm_device_check.restype = C.c_int
     lib.pm_error_string.restype = C.c_char_p
     lib.pm_error_string.argtypes = [C.c_int]
+    for name in WORKSPACE_QUERIES:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"libpaintmind_b200.so does not export {name}")
+        fn = getattr(lib, name)
+        fn.restype = C.c_int64
+        fn.argtypes = [C.c_int32] * WORKSPACE_QUERIES[name]
     for name, argtypes in EXPORTS.items():
         if not hasattr(lib, name):
             raise RuntimeError(f"libpaintmind_b200.so does not export {name}")
@@ -105,6 +125,20 @@ EXPORTS = {
     "pm_maskgit_remask": [_p, _p, _i32, _i32, _i32, _i64, _p],
     "pm_maskgit_random_mask": [_p, _i64, _p, C.c_uint64, C.c_uint64, _p, _i32, _i32, _i32, _p, _p, _p],
     "pm_ce_label_smooth": [_p, _i64, _i32, _i32, _p, _p, _f, _p, _p, _p, _p],
+    # generator backward path
+    "pm_attn_bwd": [C.POINTER(AttnBwdArgs), _p],
+    "pm_wgrad_bf16": [_p, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _i64, _i32, _p],
+    "pm_colsum_bf16": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],
+    "pm_layernorm_bwd": [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _i32, _i32, _f, _p, _p, _p],
+    "pm_swiglu_bwd": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i32, _i32, _p],
+    "pm_vq_bwd": [_p, _i64, _p, _p, _i32, _p, _i64, _p, _f, _i32, _p, _p, _p, _p],
+    "pm_unpatchify8_bwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _p],
+}
+# workspace-size queries (return int64 element counts): name -> number of int32 arguments
+WORKSPACE_QUERIES = {
+    "pm_wgrad_workspace_floats": 3,
+    "pm_colsum_workspace_floats": 2,
+    "pm_layernorm_bwd_workspace_floats": 2,
 }
 
 

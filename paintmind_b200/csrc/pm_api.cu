@@ -74,7 +74,71 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
   p.bsq = a->bsq; p.bsk = a->bsk; p.bsv = a->bsv; p.bso = a->bso;
   p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.head_dim = a->head_dim;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.lse = a->lse;
   return pm_attn_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int pm_attn_bwd(const pm_attn_bwd_args* a, void* stream) {
+  if (a == nullptr || a->o == nullptr || a->delta == nullptr) return PM_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = pm_attn_delta_launch(a->o, a->ldo, a->bso, a->d_o, a->lddo, a->bsdo, a->B, a->H, a->Nq, a->delta, st);
+  if (rc != 0) return rc;
+  AttnBwdParams p;
+  p.q = a->q; p.k = a->k; p.v = a->v; p.dO = a->d_o; p.dq = a->dq; p.dk = a->dk; p.dv = a->dv;
+  p.lse = a->lse; p.delta = a->delta;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.lddo = a->lddo; p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.bsq = a->bsq; p.bsk = a->bsk; p.bsv = a->bsv; p.bsdo = a->bsdo; p.bsdq = a->bsdq; p.bsdk = a->bsdk; p.bsdv = a->bsdv;
+  p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.head_dim = a->head_dim;
+  p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  return pm_attn_bwd_launch(p, st);
+}
+
+int64_t pm_wgrad_workspace_floats(int32_t M, int32_t N, int32_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return static_cast<int64_t>(pm_wgrad_splits(M, N, K)) * N * K;
+}
+
+int pm_wgrad_bf16(const void* dy, int64_t lddy, const void* x, int64_t ldx, int32_t M, int32_t N, int32_t K, float* work,
+                  float* out, int64_t ld_out, int32_t accumulate, void* stream) {
+  WgradParams p;
+  p.dy = dy; p.x = x; p.work = work; p.out = out; p.lddy = lddy; p.ldx = ldx; p.ld_out = ld_out;
+  p.M = M; p.N = N; p.K = K; p.splits = 0; p.accumulate = accumulate; p.scale = 1.0f;
+  return pm_wgrad_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int64_t pm_colsum_workspace_floats(int32_t M, int32_t N) {
+  if (M <= 0 || N <= 0) return 0;
+  return static_cast<int64_t>(pm_colsum_rows(M, N)) * N;
+}
+
+int pm_colsum_bf16(const void* x, int64_t ld, int32_t M, int32_t N, float* work, float* out, int32_t accumulate, void* stream) {
+  return pm_colsum_launch(x, ld, M, N, work, out, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int64_t pm_layernorm_bwd_workspace_floats(int32_t M, int32_t D) {
+  if (M <= 0 || D <= 0) return 0;
+  return static_cast<int64_t>(pm_ln_bwd_blocks(M)) * 2 * D;
+}
+
+int pm_layernorm_bwd(const void* dn, int64_t lddn, const void* x, int64_t ldx, const float* gamma, const void* dres, int64_t ldres,
+                     void* dx, int64_t lddx, int32_t M, int32_t D, float eps, float* work, float* dgamma_dbeta, void* stream) {
+  return pm_ln_bwd_launch(dn, lddn, x, ldx, gamma, dres, ldres, dx, lddx, M, D, eps, work, dgamma_dbeta, static_cast<cudaStream_t>(stream));
+}
+
+int pm_swiglu_bwd(const void* x12, int64_t ld12, const void* dh, int64_t lddh, void* h, int64_t ldh, void* d12, int64_t ldd12,
+                  int32_t M, int32_t hp, void* stream) {
+  return pm_swiglu_bwd_launch(x12, ld12, dh, lddh, h, ldh, d12, ldd12, M, hp, static_cast<cudaStream_t>(stream));
+}
+
+int pm_vq_bwd(const float* z, int64_t ldz, const int64_t* idx, const float* E, int32_t e_dim, const float* d_out, int64_t ldd,
+              const float* d_loss, float beta, int32_t M, float* dz, void* dz_split, float* dE, void* stream) {
+  if (e_dim != 32) return PM_ERR_INVALID;
+  return pm_vq_bwd_launch(z, ldz, reinterpret_cast<const long long*>(idx), E, d_out, ldd, d_loss, beta, M, dz, dz_split, dE,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int pm_unpatchify8_bwd(const float* d_img, const float* rec, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  return pm_unpatchify_bwd_launch(d_img, rec, out, B, C, H, W, static_cast<cudaStream_t>(stream));
 }
 
 int pm_vq_codebook_prep(const float* E, int32_t n_e, int32_t e_dim, float* en, void* packed, void* stream) {

@@ -389,7 +389,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       // ---- item epilogue: O / l -> bf16 -> swizzled smem staging -> TMA store ----
       mbar_wait_a(b_pv_done, (g - 1) & 1);
       tc_fence_after();
-      const float inv_l = 1.0f / ((la.x + la.y) + (lb.x + lb.y));
+      const float l_sum = (la.x + la.y) + (lb.x + lb.y);
+      const float inv_l = 1.0f / l_sum;
+      if (p.lse != nullptr) {
+        // training forward: base-2 log-sum-exp of the scaled score row, consumed by pm_attn_bwd
+        const int qrow = it.qb * 2 * AT_BM + t * AT_BM + row_in_tile;
+        if (qrow < p.Nq) p.lse[(static_cast<size_t>(it.b) * p.H + it.h) * p.Nq + qrow] = m_used + log2f(l_sum);
+      }
       uint32_t r0[32], r1[32];
       tmem_ld_x32(tO, r0);
       tmem_ld_x32(tO + 32, r1);

@@ -1,0 +1,265 @@
+// pm_attn_bwd.cu — backward of the flash attention core on tcgen05 / TMEM (sm_100a), head_dim = 64.
+//
+// What autograd derives in the reference for modules/attention.py:52-57 (sim = einsum(q * scale, k); softmax;
+// out = einsum(attn, v)) — SURVEY.md §8f row 4.  With P = softmax(scale * Q K^T) recomputed from the forward's
+// row log-sum-exp (base 2, `lse`) and delta = rowsum(dO ⊙ O):
+//     dV = P^T dO          dS = P ⊙ (dO V^T - delta) * scale          dQ = dS K          dK = dS^T Q
+// Two launches of one kernel template, no atomics, deterministic:
+//   DKV = false : CTA = (128-query tile, head, batch), loops over key tiles.   rows = queries, columns = keys
+//                 S' = Q K_j^T,  dP' = dO V_j^T,  dQ += dS' K_j
+//   DKV = true  : CTA = (128-key tile, head, batch), loops over query tiles.  rows = keys, columns = queries
+//                 S' = K Q_i^T (= S^T),  dP' = V dO_i^T,  dV += P' dO_i,  dK += dS' Q_i
+// In both, the two score-shaped products are SS MMAs (both operands K-major, 128 x 128 x 64) into TMEM; 128 threads
+// (one per TMEM lane = row) turn them into P' and dS' (packed bf16, written back to TMEM), which then feed TS MMAs
+// (A from TMEM, B = the very same shared-memory tile re-read as an MN-major operand — no transposes anywhere).
+// TMEM (512 columns): S' [0,128) dP' [128,256) P' [256,320) dS' [320,384) acc1 [384,448) acc2 [448,512).
+#include "pm_common.cuh"
+#include "pm_kernels.h"
+
+namespace pm {
+
+constexpr int AB_T = 128;                      // tile edge (rows and columns)
+constexpr int AB_D = 64;
+constexpr int AB_TILE = AB_T * AB_D * 2;       // 16 KB
+constexpr int AB_NST = 3;                      // column-operand ring depth
+constexpr int AB_THREADS = 192;                // 4 compute warps, TMA warp, MMA warp
+constexpr int AB_SMEM = 1024 + 2 * AB_TILE + AB_NST * 2 * AB_TILE + AB_NST * 1024 + 256;
+
+__device__ __forceinline__ float ab_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool DKV>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
+                const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2,
+                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_a = smem_u32(smem_raw);
+  const uint32_t sR1 = (raw_a + 1023u) & ~1023u;
+  const uint32_t sR2 = sR1 + AB_TILE;
+  const uint32_t sC = sR2 + AB_TILE;                       // [NST][C1 16 KB | C2 16 KB]
+  const uint32_t sVec = sC + AB_NST * 2 * AB_TILE;         // [NST][lse 512 B | delta 512 B]
+  const uint32_t bars = sVec + AB_NST * 1024;
+  const uint32_t r_full = bars, c_full = bars + 8, c_empty = c_full + 8 * AB_NST, s_full = c_empty + 8 * AB_NST;
+  const uint32_t p_full = s_full + 8, acc_done = p_full + 8, tmem_slot_a = acc_done + 8;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot_a - raw_a));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int T = (DKV ? p.Nq : p.Nk) / AB_T;               // column tiles to walk
+  const size_t vec_base = (static_cast<size_t>(b) * p.H + h) * p.Nq;     // lse / delta are per query
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmR1); tma_prefetch_desc(&tmR2); tma_prefetch_desc(&tmC1); tma_prefetch_desc(&tmC2);
+    tma_prefetch_desc(&tmO1);
+    if (DKV) tma_prefetch_desc(&tmO2);
+    auto init = [](uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); };
+    init(r_full, 1);
+    for (int i = 0; i < AB_NST; ++i) { init(c_full + 8 * i, 1); init(c_empty + 8 * i, 1); }
+    init(s_full, 1);
+    init(p_full, 4);
+    init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320;
+  const uint32_t tA1 = tmem_base + 384, tA2 = tmem_base + 448;
+
+  if (warp == 4) {
+    // ===================================== TMA producer ======================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx_a(r_full, 2 * AB_TILE);
+      tma_load_3d_a(sR1, &tmR1, r_full, h * AB_D, rt * AB_T, b);
+      tma_load_3d_a(sR2, &tmR2, r_full, h * AB_D, rt * AB_T, b);
+      for (int t = 0; t < T; ++t) {
+        const int st = t % AB_NST;
+        mbar_wait_a(c_empty + 8 * st, ((t / AB_NST) & 1) ^ 1);
+        mbar_arrive_expect_tx_a(c_full + 8 * st, 2 * AB_TILE + (DKV ? 1024 : 0));
+        tma_load_3d_a(sC + st * 2 * AB_TILE, &tmC1, c_full + 8 * st, h * AB_D, t * AB_T, b);
+        tma_load_3d_a(sC + st * 2 * AB_TILE + AB_TILE, &tmC2, c_full + 8 * st, h * AB_D, t * AB_T, b);
+        if (DKV) {
+          // the 128 per-query (lse, delta) values of this column tile
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(sVec + st * 1024), "l"(reinterpret_cast<uint64_t>(p.lse + vec_base + t * AB_T)), "r"(512u), "r"(c_full + 8 * st)
+                       : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(sVec + st * 1024 + 512), "l"(reinterpret_cast<uint64_t>(p.delta + vec_base + t * AB_T)), "r"(512u), "r"(c_full + 8 * st)
+                       : "memory");
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================== MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_ss = umma_idesc_bf16(AB_T, AB_T, 0, 0);     // both K-major
+      constexpr uint32_t idesc_ts = umma_idesc_bf16(AB_T, AB_D, 0, 1);     // A from TMEM, B MN-major
+      const uint64_t dr1 = umma_desc_sw128(sR1), dr2 = umma_desc_sw128(sR2);
+      mbar_wait_a(r_full, 0);
+      auto issue_ts = [&](int t) {
+        const int st = t % AB_NST;
+        const uint64_t dc1 = umma_desc_sw128(sC + st * 2 * AB_TILE), dc2 = umma_desc_sw128(sC + st * 2 * AB_TILE + AB_TILE);
+#pragma unroll
+        for (int kk = 0; kk < AB_T / 16; ++kk) {
+          umma_ts(tA1, tDS + 8 * kk, dc1 + kk * (2048 >> 4), idesc_ts, (t | kk) != 0 ? 1u : 0u);
+          if (DKV) umma_ts(tA2, tP + 8 * kk, dc2 + kk * (2048 >> 4), idesc_ts, (t | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit_a(acc_done);
+        umma_commit_a(c_empty + 8 * st);
+      };
+      for (int t = 0; t < T; ++t) {
+        const int st = t % AB_NST;
+        mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);
+        if (t > 0) mbar_wait_a(p_full, (t - 1) & 1);        // P'/dS'(t-1) written, S'/dP'(t-1) consumed
+        tc_fence_after();
+        const uint64_t dc1 = umma_desc_sw128(sC + st * 2 * AB_TILE), dc2 = umma_desc_sw128(sC + st * 2 * AB_TILE + AB_TILE);
+#pragma unroll
+        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tS, dr1 + 2 * k, dc1 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tDP, dr2 + 2 * k, dc2 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+        umma_commit_a(s_full);
+        if (t > 0) issue_ts(t - 1);
+      }
+      mbar_wait_a(p_full, (T - 1) & 1);
+      tc_fence_after();
+      issue_ts(T - 1);
+    }
+  } else {
+    // ===================================== compute warps =====================================
+    const int q = warp;                                       // TMEM lane quarter
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float c = p.scale_log2, sc = p.scale;
+    float lse_row = 0.f, dl_row = 0.f;
+    if (!DKV) {
+      lse_row = p.lse[vec_base + rt * AB_T + row_in_tile];
+      dl_row = p.delta[vec_base + rt * AB_T + row_in_tile];
+    }
+    for (int t = 0; t < T; ++t) {
+      const int st = t % AB_NST;
+      const float* lse_s = reinterpret_cast<const float*>(smem_raw + (sVec + st * 1024 - raw_a));
+      const float* dl_s = lse_s + 128;
+      mbar_wait_a(s_full, t & 1);
+      tc_fence_after();
+      if (DKV) mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);     // this thread reads the TMA-written (lse, delta) vectors itself
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t s[32], dp[32];
+        tmem_ld_x32(tS + lane_off + ch * 32, s);
+        tmem_ld_x32(tDP + lane_off + ch * 32, dp);
+        tmem_ld_wait();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float l0 = lse_row, l1 = lse_row, d0 = dl_row, d1 = dl_row;
+          if (DKV) {
+            const float2 lv = *reinterpret_cast<const float2*>(lse_s + ch * 32 + e);
+            const float2 dv = *reinterpret_cast<const float2*>(dl_s + ch * 32 + e);
+            l0 = lv.x; l1 = lv.y; d0 = dv.x; d1 = dv.y;
+          }
+          const float p0 = ab_ex2(fmaf(__uint_as_float(s[e]), c, -l0));
+          const float p1 = ab_ex2(fmaf(__uint_as_float(s[e + 1]), c, -l1));
+          const float g0 = p0 * (__uint_as_float(dp[e]) - d0) * sc;
+          const float g1 = p1 * (__uint_as_float(dp[e + 1]) - d1) * sc;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          dk[e >> 1] = pack_bf16x2(g0, g1);
+        }
+        if (ch == 0 && t > 0) {
+          // the TS MMAs of the previous step read P' / dS' until this fires
+          mbar_wait_a(acc_done, (t - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_x16(tDS + lane_off + ch * 16, dk);
+        if (DKV) tmem_st_x16(tP + lane_off + ch * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(p_full);
+    }
+    // ---- epilogue: accumulators -> bf16 -> swizzled staging (the row-operand tiles are dead by now) -> TMA store ----
+    mbar_wait_a(acc_done, (T - 1) & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int a = 0; a < (DKV ? 2 : 1); ++a) {
+      uint32_t r0[32], r1[32];
+      tmem_ld_x32((a == 0 ? tA1 : tA2) + lane_off, r0);
+      tmem_ld_x32((a == 0 ? tA1 : tA2) + lane_off + 32, r1);
+      tmem_ld_wait();
+      uint8_t* stg = smem_raw + ((a == 0 ? sR1 : sR2) - raw_a) + row_in_tile * 128;
+#pragma unroll
+      for (int jv = 0; jv < 4; ++jv) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r0[jv * 8 + 0]), __uint_as_float(r0[jv * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(r0[jv * 8 + 2]), __uint_as_float(r0[jv * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(r0[jv * 8 + 4]), __uint_as_float(r0[jv * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(r0[jv * 8 + 6]), __uint_as_float(r0[jv * 8 + 7]));
+        *reinterpret_cast<uint4*>(stg + ((jv ^ (row_in_tile & 7)) << 4)) = o;
+      }
+#pragma unroll
+      for (int jv = 0; jv < 4; ++jv) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r1[jv * 8 + 0]), __uint_as_float(r1[jv * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(r1[jv * 8 + 2]), __uint_as_float(r1[jv * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(r1[jv * 8 + 4]), __uint_as_float(r1[jv * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(r1[jv * 8 + 6]), __uint_as_float(r1[jv * 8 + 7]));
+        *reinterpret_cast<uint4*>(stg + (((4 + jv) ^ (row_in_tile & 7)) << 4)) = o;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                   ::"l"(reinterpret_cast<uint64_t>(&tmO1)), "r"(sR1), "r"(h * AB_D), "r"(rt * AB_T), "r"(b) : "memory");
+      if (DKV)
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmO2)), "r"(sR2), "r"(h * AB_D), "r"(rt * AB_T), "r"(b) : "memory");
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream) {
+  if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.dO == nullptr || p.lse == nullptr || p.delta == nullptr) return PM_ERR_INVALID;
+  if (p.dq == nullptr || p.dk == nullptr || p.dv == nullptr) return PM_ERR_INVALID;
+  if (p.B <= 0 || p.H <= 0 || p.Nq <= 0 || p.Nk <= 0 || (p.Nq % AB_T) != 0 || (p.Nk % AB_T) != 0 || p.head_dim != AB_D) return PM_ERR_INVALID;
+  CUtensorMap tQ, tK, tV, tDO, tDQ, tDK, tDV;
+  int rc;
+  const uint64_t inner = static_cast<uint64_t>(p.H) * AB_D;
+  if ((rc = pm_make_tmap_3d(&tQ, p.q, 2, p.B, p.Nq, inner, p.ldq, p.bsq, AB_T, AB_D)) != PM_OK) return rc;
+  if ((rc = pm_make_tmap_3d(&tK, p.k, 2, p.B, p.Nk, inner, p.ldk, p.bsk, AB_T, AB_D)) != PM_OK) return rc;
+  if ((rc = pm_make_tmap_3d(&tV, p.v, 2, p.B, p.Nk, inner, p.ldv, p.bsv, AB_T, AB_D)) != PM_OK) return rc;
+  if ((rc = pm_make_tmap_3d(&tDO, p.dO, 2, p.B, p.Nq, inner, p.lddo, p.bsdo, AB_T, AB_D)) != PM_OK) return rc;
+  if ((rc = pm_make_tmap_3d(&tDQ, p.dq, 2, p.B, p.Nq, inner, p.lddq, p.bsdq, AB_T, AB_D)) != PM_OK) return rc;
+  if ((rc = pm_make_tmap_3d(&tDK, p.dk, 2, p.B, p.Nk, inner, p.lddk, p.bsdk, AB_T, AB_D)) != PM_OK) return rc;
+  if ((rc = pm_make_tmap_3d(&tDV, p.dv, 2, p.B, p.Nk, inner, p.lddv, p.bsdv, AB_T, AB_D)) != PM_OK) return rc;
+  static bool attr_a[PM_MAX_DEVICES] = {}, attr_b[PM_MAX_DEVICES] = {};
+  if ((rc = pm_ensure_dyn_smem(attn_bwd_kernel<false>, AB_SMEM, attr_a)) != 0) return rc;
+  if ((rc = pm_ensure_dyn_smem(attn_bwd_kernel<true>, AB_SMEM, attr_b)) != 0) return rc;
+  // dK / dV: rows = keys (R1 = K, R2 = V), columns = queries (C1 = Q, C2 = dO); acc1 = dS' Q = dK, acc2 = P' dO = dV
+  attn_bwd_kernel<true><<<dim3(p.Nk / AB_T, p.H, p.B), AB_THREADS, AB_SMEM, stream>>>(tK, tV, tQ, tDO, tDK, tDV, p);
+  if ((rc = static_cast<int>(cudaGetLastError())) != 0) return rc;
+  // dQ: rows = queries (R1 = Q, R2 = dO), columns = keys (C1 = K, C2 = V); acc1 = dS' K = dQ
+  attn_bwd_kernel<false><<<dim3(p.Nq / AB_T, p.H, p.B), AB_THREADS, AB_SMEM, stream>>>(tQ, tDO, tK, tV, tDQ, tDQ, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pm

@@ -191,6 +191,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand wider than one 64-element swizzle atom along M/N: `lbo_bytes` = distance between consecutive
+// 64-element groups (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units); SBO = 1024 B per 8 k-rows.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major,
                                                        int b_mn_major) {
@@ -365,6 +377,10 @@ int pm_make_tmap_2d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t 
 int pm_make_tmap_3d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t batch,
                     uint64_t rows, uint64_t cols, uint64_t ld_row, uint64_t ld_batch,
                     uint32_t box_rows, uint32_t box_cols);
+// same with a box that spans `box_batch` entries of the outermost dimension
+int pm_make_tmap_3d_box(CUtensorMap* map, const void* base, int elt_bytes, uint64_t batch, uint64_t rows,
+                        uint64_t cols, uint64_t ld_row, uint64_t ld_batch, uint32_t box_batch, uint32_t box_rows,
+                        uint32_t box_cols);
 
 }  // namespace pm
 

@@ -40,6 +40,35 @@ struct AttnParams {
   int64_t bsq, bsk, bsv, bso;      // batch stride in elements
   int B, H, Nq, Nk, head_dim;
   float scale_log2;                // softmax scale * log2(e)
+  float* lse;                      // optional [B, H, Nq] fp32 out: base-2 log-sum-exp of the scaled scores (training forward)
+};
+
+struct AttnBwdParams {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* dO;
+  void* dq;
+  void* dk;
+  void* dv;
+  const float* lse;                // [B, H, Nq] from the forward
+  const float* delta;              // [B, H, Nq] rowsum(dO * O)
+  int64_t ldq, ldk, ldv, lddo, lddq, lddk, lddv;
+  int64_t bsq, bsk, bsv, bsdo, bsdq, bsdk, bsdv;
+  int B, H, Nq, Nk, head_dim;
+  float scale, scale_log2;
+};
+
+struct WgradParams {
+  const void* dy;                  // bf16 [M, N] (row pitch lddy >= N rounded up to 64)
+  const void* x;                   // bf16 [M, K]
+  float* work;                     // fp32 [splits, N, K]
+  float* out;                      // fp32 [N, K], row pitch ld_out
+  int64_t lddy, ldx, ld_out;
+  int M, N, K;
+  int splits;                      // 0 = auto (pm_wgrad_splits)
+  int accumulate;                  // 1: out += result
+  float scale;
 };
 
 struct VqParams {
@@ -100,6 +129,22 @@ int pm_maskgit_random_mask_launch(const float* z, int64_t ldz, const float* nois
 int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, const long long* label, const float* mask,
                               float eps, float* row_loss, float* loss_out, double* sums_out, cudaStream_t stream);
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
+int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream);
+int pm_attn_delta_launch(const void* o, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H, int N,
+                         float* delta, cudaStream_t stream);
+int pm_wgrad_splits(int M, int N, int K);
+int pm_wgrad_launch(const WgradParams& p, cudaStream_t stream);
+int pm_colsum_rows(int M, int N);
+int pm_colsum_launch(const void* x, int64_t ld, int M, int N, float* partial, float* out, int accumulate, cudaStream_t stream);
+int pm_ln_bwd_blocks(int M);
+int pm_ln_bwd_launch(const void* dn, int64_t lddn, const void* x, int64_t ldx, const float* gamma, const void* dres,
+                     int64_t ldres, void* dx, int64_t lddx, int M, int D, float eps, float* part, float* dgamma_dbeta,
+                     cudaStream_t stream);
+int pm_swiglu_bwd_launch(const void* x12, int64_t ld12, const void* dh, int64_t lddh, void* h, int64_t ldh, void* d12,
+                         int64_t ldd12, int M, int hp, cudaStream_t stream);
+int pm_vq_bwd_launch(const float* z, int64_t ldz, const long long* idx, const float* E, const float* d_out, int64_t ldd,
+                     const float* d_loss, float beta, int M, float* dz, void* dz_split, float* dE, cudaStream_t stream);
+int pm_unpatchify_bwd_launch(const float* g, const float* rec, void* out, int B, int C, int H, int W, cudaStream_t stream);
 int pm_vq_codebook_prep_launch(const float* E, int n_e, float* en, void* packed, cudaStream_t stream);
 int pm_vq_launch(const VqParams& p, cudaStream_t stream);
 int pm_vq_gather_launch(const long long* idx, int M, int n_rows, const float* table, int normalize,

@@ -41,6 +41,12 @@ int pm_make_tmap_2d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t 
 int pm_make_tmap_3d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t batch, uint64_t rows,
                     uint64_t cols, uint64_t ld_row, uint64_t ld_batch, uint32_t box_rows,
                     uint32_t box_cols) {
+  return pm_make_tmap_3d_box(map, base, elt_bytes, batch, rows, cols, ld_row, ld_batch, 1, box_rows, box_cols);
+}
+
+int pm_make_tmap_3d_box(CUtensorMap* map, const void* base, int elt_bytes, uint64_t batch, uint64_t rows,
+                        uint64_t cols, uint64_t ld_row, uint64_t ld_batch, uint32_t box_batch, uint32_t box_rows,
+                        uint32_t box_cols) {
   PFN_encodeTiled enc;
   int rc = pm_get_encode_fn(&enc);
   if (rc != PM_OK) return rc;
@@ -50,7 +56,7 @@ int pm_make_tmap_3d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t 
   if (box_cols * elt_bytes != 128 || box_rows > 256) return PM_ERR_INVALID;
   cuuint64_t gdim[3] = {cols, rows, batch};
   cuuint64_t gstride[2] = {ld_row * elt_bytes, ld_batch * elt_bytes};
-  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t box[3] = {box_cols, box_rows, box_batch};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dtype_of(elt_bytes), 3, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -267,3 +267,123 @@ def ce_label_smooth(logits2d, label, mask, label_smoothing, *, row_loss, loss_ou
                                               float(label_smoothing), _ptr(row_loss), _ptr(loss_out), _ptr(sums_out),
                                               _stream()), "pm_ce_label_smooth")
     _prof_end(t0, ("ce_label_smooth", M, V))
+
+
+# ------------------------------------------------------------------------------------------------
+# generator backward path
+# ------------------------------------------------------------------------------------------------
+_WORK = {}
+
+
+def _workspace(name, nfloats, device):
+    """fp32 scratch reused across calls (split-K partial tiles, column-sum partials)."""
+    key = (name, str(device))
+    t = _WORK.get(key)
+    if t is None or t.numel() < nfloats:
+        t = torch.empty(max(int(nfloats), 1), device=device, dtype=torch.float32)
+        _WORK[key] = t
+    return t
+
+
+def attention_train(q, k, v, o, heads, scale, lse):
+    """attention() that also writes the base-2 log-sum-exp rows [B, heads, Nq] needed by attention_bwd."""
+    _require_cuda(q, k, v, o, lse)
+    args = _lib.AttnArgs()
+    args.q, args.k, args.v, args.o = _ptr(q), _ptr(k), _ptr(v), _ptr(o)
+    args.ldq, args.ldk, args.ldv, args.ldo = q.stride(1), k.stride(1), v.stride(1), o.stride(1)
+    args.bsq, args.bsk, args.bsv, args.bso = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
+    args.scale = float(scale)
+    args.lse = _ptr(lse)
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_attn_fwd(C.byref(args), _stream()), "pm_attn_fwd")
+    _prof_end(t0, ("attention", args.B, args.H, args.Nq, args.Nk))
+    return o
+
+
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, heads, scale):
+    """dq, dk, dv of softmax(scale q k^T) v; all [B, N, >= heads*64] bf16 views with last stride 1."""
+    _require_cuda(q, k, v, o, d_o, lse, dq, dk, dv)
+    B, Nq, Nk = q.shape[0], q.shape[1], k.shape[1]
+    delta = _workspace("attn_delta", B * heads * Nq, q.device)
+    a = _lib.AttnBwdArgs()
+    a.q, a.k, a.v, a.o, a.d_o = _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(d_o)
+    a.lse, a.delta, a.dq, a.dk, a.dv = _ptr(lse), _ptr(delta), _ptr(dq), _ptr(dk), _ptr(dv)
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddo = q.stride(1), k.stride(1), v.stride(1), o.stride(1), d_o.stride(1)
+    a.lddq, a.lddk, a.lddv = dq.stride(1), dk.stride(1), dv.stride(1)
+    a.bsq, a.bsk, a.bsv, a.bso, a.bsdo = q.stride(0), k.stride(0), v.stride(0), o.stride(0), d_o.stride(0)
+    a.bsdq, a.bsdk, a.bsdv = dq.stride(0), dk.stride(0), dv.stride(0)
+    a.B, a.H, a.Nq, a.Nk, a.head_dim = B, heads, Nq, Nk, 64
+    a.scale = float(scale)
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_attn_bwd(C.byref(a), _stream()), "pm_attn_bwd")
+    _prof_end(t0, ("attention_bwd", B, heads, Nq, Nk), 3)
+
+
+def wgrad(dy, x, out, n=None, k=None, accumulate=False):
+    """out[N, K] (+)= dy[M, :N]^T @ x[M, :K]  (fp32 out; dy, x bf16 token-major)."""
+    _require_cuda(dy, x, out)
+    M = dy.shape[0]
+    N = n if n is not None else dy.shape[1]
+    K = k if k is not None else x.shape[1]
+    lib = _lib.load()
+    work = _workspace("wgrad", lib.pm_wgrad_workspace_floats(M, N, K), dy.device)
+    t0 = _prof_begin()
+    _lib.check(lib.pm_wgrad_bf16(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), M, N, K, _ptr(work), _ptr(out), out.stride(0),
+                                 int(bool(accumulate)), _stream()), "pm_wgrad_bf16")
+    _prof_end(t0, ("wgrad", M, N, K), 2)
+    return out
+
+
+def colsum(x, out, accumulate=False):
+    """out[N] (+)= sum over rows of bf16 x[M, N]."""
+    _require_cuda(x, out)
+    M, N = x.shape
+    lib = _lib.load()
+    work = _workspace("colsum", lib.pm_colsum_workspace_floats(M, N), x.device)
+    t0 = _prof_begin()
+    _lib.check(lib.pm_colsum_bf16(_ptr(x), x.stride(0), M, N, _ptr(work), _ptr(out), int(bool(accumulate)), _stream()), "pm_colsum_bf16")
+    _prof_end(t0, ("colsum", M, N), 2)
+    return out
+
+
+def layernorm_bwd(dn, x, gamma, dx, dgamma_dbeta, dres=None, eps=1e-5):
+    """dx = LayerNorm'(x)^T dn (+ dres); dgamma_dbeta [2, D] fp32 = (sum dn * xhat, sum dn)."""
+    _require_cuda(dn, x, gamma, dx, dgamma_dbeta)
+    M, D = x.shape
+    lib = _lib.load()
+    work = _workspace("ln_bwd", lib.pm_layernorm_bwd_workspace_floats(M, D), x.device)
+    t0 = _prof_begin()
+    _lib.check(lib.pm_layernorm_bwd(_ptr(dn), dn.stride(0), _ptr(x), x.stride(0), _ptr(gamma), _ptr(dres),
+                                    dres.stride(0) if dres is not None else 0, _ptr(dx), dx.stride(0), M, D, float(eps),
+                                    _ptr(work), _ptr(dgamma_dbeta), _stream()), "pm_layernorm_bwd")
+    _prof_end(t0, ("layernorm_bwd", M, D), 2)
+    return dx
+
+
+def swiglu_bwd(x12, dh, h, d12):
+    _require_cuda(x12, dh, d12)
+    M, hp = dh.shape
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_swiglu_bwd(_ptr(x12), x12.stride(0), _ptr(dh), dh.stride(0), _ptr(h), h.stride(0) if h is not None else 0,
+                                         _ptr(d12), d12.stride(0), M, hp, _stream()), "pm_swiglu_bwd")
+    _prof_end(t0, ("swiglu_bwd", M, hp))
+
+
+def vq_bwd(z, idx, E, d_out, d_loss, beta, dz=None, dz_split=None, dE=None):
+    _require_cuda(z, idx, E)
+    M = z.shape[0]
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_vq_bwd(_ptr(z), z.stride(0), _ptr(idx), _ptr(E), E.shape[1], _ptr(d_out),
+                                     d_out.stride(0) if d_out is not None else 0, _ptr(d_loss), float(beta), M,
+                                     _ptr(dz), _ptr(dz_split), _ptr(dE), _stream()), "pm_vq_bwd")
+    _prof_end(t0, ("vq_bwd", M))
+
+
+def unpatchify8_bwd(d_img, rec, out):
+    _require_cuda(d_img, rec, out)
+    B, Cc, H, W = d_img.shape
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_unpatchify8_bwd(_ptr(d_img), _ptr(rec), _ptr(out), B, Cc, H, W, _stream()), "pm_unpatchify8_bwd")
+    _prof_end(t0, ("unpatchify8_bwd", B))
+    return out
