@@ -111,6 +111,8 @@ typedef struct pm_attn_args {
   float scale;                     /* dim_head ** -0.5 (attention.py:31) */
   float* lse;                      /* optional out [B, H, Nq] fp32: log2-sum-exp2 of the scaled score rows, kept by a
                                       training forward for pm_attn_bwd; NULL for inference */
+  float* o32;                      /* optional out: fp32 copy of O, [B, Nq, ldo32] dense over the batch (training forward: */
+  int64_t ldo32;                   /* keeps delta = rowsum(dO * O) of the backward free of O's bf16 rounding); else NULL   */
 } pm_attn_args;
 
 int pm_attn_fwd(const pm_attn_args* args, void* stream);
@@ -246,7 +248,7 @@ typedef struct pm_attn_bwd_args {
   const void* q;
   const void* k;
   const void* v;
-  const void* o;      /* forward output */
+  const void* o;      /* forward output: bf16, or the fp32 copy (o32 of pm_attn_fwd) when o_is_f32 */
   const void* d_o;    /* gradient of o */
   const float* lse;   /* [B, H, Nq] from pm_attn_fwd */
   float* delta;       /* [B, H, Nq] scratch */
@@ -257,6 +259,7 @@ typedef struct pm_attn_bwd_args {
   int64_t bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv;
   int32_t B, H, Nq, Nk, head_dim;
   float scale;
+  int32_t o_is_f32;
 } pm_attn_bwd_args;
 
 int pm_attn_bwd(const pm_attn_bwd_args* args, void* stream);

@@ -115,3 +115,30 @@ def vqmodel_decode(z, sd, cfg, clamp=True):
     x = F.linear(z, sd["post_quant.weight"], sd["post_quant.bias"])
     x = decoder_forward(x, sd, cfg["dec"])
     return x.clamp(-1.0, 1.0) if clamp else x
+
+
+# ------------------------------------------------------------------------------------------------
+# training forward (what VQGANTrainer differentiates, utils/trainer.py:205-217): same functions, run under
+# autograd on a state dict whose tensors require grad; only the quantizer needs its detach structure spelled out.
+# ------------------------------------------------------------------------------------------------
+def vq_forward_train(z, codebook, beta=0.25, idx=None):
+    """VectorQuantizer.forward with the reference's stop-gradients (stage1/quantize.py:18-38).  `idx` overrides the
+    argmin (tests pass the indices the CUDA path chose, so that near-tie flips do not enter a gradient comparison)."""
+    zn = F.normalize(z, p=2, dim=-1)                                           # :19
+    if idx is None:
+        zf = zn.reshape(-1, codebook.shape[1])
+        en = F.normalize(codebook, p=2, dim=-1)                                # :21
+        d = zf.pow(2).sum(dim=1, keepdim=True) + en.pow(2).sum(dim=1) - 2 * (zf @ en.t())
+        idx = torch.argmin(d, dim=1).view(zn.shape[:-1])                       # :28
+    z_q = F.normalize(codebook[idx], p=2, dim=-1)                              # :29-30
+    loss = beta * torch.mean((z_q.detach() - zn) ** 2) + torch.mean((z_q - zn.detach()) ** 2)   # :33
+    z_q = zn + (z_q - zn).detach()                                             # :36
+    return z_q, loss, idx
+
+
+def vqmodel_forward_train(img, sd, cfg, idx=None):
+    """VQModel.forward (stage1/vqmodel.py:32-36) -> (rec, codebook loss, indices), differentiable."""
+    x = encoder_forward(img, sd, cfg["enc"])
+    x = F.linear(x, sd["prev_quant.weight"], sd["prev_quant.bias"])
+    z_q, loss, idx = vq_forward_train(x, sd["quantize.embedding.weight"], cfg["beta"], idx)
+    return vqmodel_decode(z_q, sd, cfg), loss, idx

@@ -75,13 +75,16 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
   p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.head_dim = a->head_dim;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.lse = a->lse;
+  p.o32 = a->o32;
+  p.ldo32 = a->ldo32;
+  if (p.o32 != nullptr && ((p.ldo32 % 4) != 0 || (reinterpret_cast<uintptr_t>(p.o32) & 15) != 0)) return PM_ERR_INVALID;
   return pm_attn_launch(p, static_cast<cudaStream_t>(stream));
 }
 
 int pm_attn_bwd(const pm_attn_bwd_args* a, void* stream) {
   if (a == nullptr || a->o == nullptr || a->delta == nullptr) return PM_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = pm_attn_delta_launch(a->o, a->ldo, a->bso, a->d_o, a->lddo, a->bsdo, a->B, a->H, a->Nq, a->delta, st);
+  int rc = pm_attn_delta_launch(a->o, a->o_is_f32, a->ldo, a->bso, a->d_o, a->lddo, a->bsdo, a->B, a->H, a->Nq, a->delta, st);
   if (rc != 0) return rc;
   AttnBwdParams p;
   p.q = a->q; p.k = a->k; p.v = a->v; p.dO = a->d_o; p.dq = a->dq; p.dk = a->dk; p.dv = a->dv;

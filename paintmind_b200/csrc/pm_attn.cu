@@ -401,6 +401,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_ld_x32(tO + 32, r1);
       tmem_ld_wait();
       // (O_t is free again: the next item's first P V is only issued after this thread's next p_full arrival)
+      if (p.o32 != nullptr) {
+        // training forward: an fp32 copy of the output rows, so that delta = rowsum(dO * O) of the backward pass is not
+        // limited by O's bf16 rounding (dS = P (dP - delta) cancels to ~1e-3 of its terms when attention is diffuse)
+        const int qrow = it.qb * 2 * AT_BM + t * AT_BM + row_in_tile;
+        if (qrow < p.Nq) {
+          float4* dst = reinterpret_cast<float4*>(p.o32 + (static_cast<size_t>(it.b) * p.Nq + qrow) * p.ldo32 + it.h * AT_D);
+#pragma unroll
+          for (int jv = 0; jv < 8; ++jv) {
+            dst[jv] = make_float4(__uint_as_float(r0[jv * 4 + 0]) * inv_l, __uint_as_float(r0[jv * 4 + 1]) * inv_l,
+                                  __uint_as_float(r0[jv * 4 + 2]) * inv_l, __uint_as_float(r0[jv * 4 + 3]) * inv_l);
+            dst[8 + jv] = make_float4(__uint_as_float(r1[jv * 4 + 0]) * inv_l, __uint_as_float(r1[jv * 4 + 1]) * inv_l,
+                                      __uint_as_float(r1[jv * 4 + 2]) * inv_l, __uint_as_float(r1[jv * 4 + 3]) * inv_l);
+          }
+        }
+      }
       if (q == 0 && lane == 0) tma_store_wait_read<0>();      // previous item's store has left the staging tile
       named_bar_sync(1 + t, 128);
 #pragma unroll

@@ -213,21 +213,27 @@ int pm_swiglu_bwd_launch(const void* x12, int64_t ld12, const void* dh, int64_t 
 // delta[b, h, n] = sum_d dO[b, n, h*64 + d] * O[b, n, h*64 + d]   (the softmax-backward row term).
 // One warp per token, 8 columns per lane per pass; a head = 8 consecutive lanes.
 // ----------------------------------------------------------------------------------------------
+template <bool O32>
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, int64_t bso, const __nv_bfloat16* __restrict__ dO, int64_t lddo,
+attn_delta_kernel(const void* __restrict__ o_, int64_t ldo, int64_t bso, const __nv_bfloat16* __restrict__ dO, int64_t lddo,
                   int64_t bsdo, int B, int H, int N, float* __restrict__ delta) {
   const long long tok = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tok >= static_cast<long long>(B) * N) return;
   const int b = static_cast<int>(tok / N), n = static_cast<int>(tok % N);
-  const __nv_bfloat16* orow = o + b * bso + static_cast<int64_t>(n) * ldo;
   const __nv_bfloat16* drow = dO + b * bsdo + static_cast<int64_t>(n) * lddo;
   for (int c0 = 0; c0 < H * 64; c0 += 256) {
     const int c = c0 + lane * 8;
     float s = 0.f;
     if (c < H * 64) {
       float a[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(orow + c), a);
+      if (O32) {
+        const float* orow = reinterpret_cast<const float*>(o_) + b * bso + static_cast<int64_t>(n) * ldo + c;
+        const float4 a0 = *reinterpret_cast<const float4*>(orow), a1 = *reinterpret_cast<const float4*>(orow + 4);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      } else {
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(o_) + b * bso + static_cast<int64_t>(n) * ldo + c), a);
+      }
       unpack8(*reinterpret_cast<const uint4*>(drow + c), d);
 #pragma unroll
       for (int k = 0; k < 8; ++k) s = fmaf(a[k], d[k], s);
@@ -239,13 +245,16 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo, int64_t bso,
   }
 }
 
-int pm_attn_delta_launch(const void* o, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H, int N,
-                         float* delta, cudaStream_t stream) {
+int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H,
+                         int N, float* delta, cudaStream_t stream) {
   if (o == nullptr || dO == nullptr || delta == nullptr || B <= 0 || H <= 0 || N <= 0) return PM_ERR_INVALID;
   if ((ldo % 8) != 0 || (lddo % 8) != 0 || (bso % 8) != 0 || (bsdo % 8) != 0) return PM_ERR_INVALID;
   const long long threads = static_cast<long long>(B) * N * 32;
-  attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(o), ldo, bso, reinterpret_cast<const __nv_bfloat16*>(dO), lddo, bsdo, B, H, N, delta);
+  const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+  if (o_is_f32)
+    attn_delta_kernel<true><<<blocks, 256, 0, stream>>>(o, ldo, bso, reinterpret_cast<const __nv_bfloat16*>(dO), lddo, bsdo, B, H, N, delta);
+  else
+    attn_delta_kernel<false><<<blocks, 256, 0, stream>>>(o, ldo, bso, reinterpret_cast<const __nv_bfloat16*>(dO), lddo, bsdo, B, H, N, delta);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -41,6 +41,8 @@ struct AttnParams {
   int B, H, Nq, Nk, head_dim;
   float scale_log2;                // softmax scale * log2(e)
   float* lse;                      // optional [B, H, Nq] fp32 out: base-2 log-sum-exp of the scaled scores (training forward)
+  float* o32;                      // optional [B, Nq, ldo32] fp32 copy of O (training forward; feeds delta of the backward)
+  int64_t ldo32;
 };
 
 struct AttnBwdParams {
@@ -130,8 +132,8 @@ int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, con
                               float eps, float* row_loss, float* loss_out, double* sums_out, cudaStream_t stream);
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
 int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream);
-int pm_attn_delta_launch(const void* o, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H, int N,
-                         float* delta, cudaStream_t stream);
+int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H,
+                         int N, float* delta, cudaStream_t stream);
 int pm_wgrad_splits(int M, int N, int K);
 int pm_wgrad_launch(const WgradParams& p, cudaStream_t stream);
 int pm_colsum_rows(int M, int N);

@@ -285,9 +285,10 @@ def _workspace(name, nfloats, device):
     return t
 
 
-def attention_train(q, k, v, o, heads, scale, lse):
-    """attention() that also writes the base-2 log-sum-exp rows [B, heads, Nq] needed by attention_bwd."""
-    _require_cuda(q, k, v, o, lse)
+def attention_train(q, k, v, o, heads, scale, lse, o32=None):
+    """attention() that also writes the base-2 log-sum-exp rows [B, heads, Nq] needed by attention_bwd and, optionally,
+    an fp32 copy of the output ([B, Nq, heads*64] contiguous) for an accurate softmax-backward row term."""
+    _require_cuda(q, k, v, o, lse, o32)
     args = _lib.AttnArgs()
     args.q, args.k, args.v, args.o = _ptr(q), _ptr(k), _ptr(v), _ptr(o)
     args.ldq, args.ldk, args.ldv, args.ldo = q.stride(1), k.stride(1), v.stride(1), o.stride(1)
@@ -295,6 +296,10 @@ def attention_train(q, k, v, o, heads, scale, lse):
     args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
     args.scale = float(scale)
     args.lse = _ptr(lse)
+    if o32 is not None:
+        if o32.dtype != torch.float32 or not o32.is_contiguous():
+            raise RuntimeError("attention_train: o32 must be a contiguous fp32 [B, Nq, heads*64] tensor")
+        args.o32, args.ldo32 = _ptr(o32), o32.stride(1)
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_attn_fwd(C.byref(args), _stream()), "pm_attn_fwd")
     _prof_end(t0, ("attention", args.B, args.H, args.Nq, args.Nk))
@@ -315,6 +320,7 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, heads, scale):
     a.bsdq, a.bsdk, a.bsdv = dq.stride(0), dk.stride(0), dv.stride(0)
     a.B, a.H, a.Nq, a.Nk, a.head_dim = B, heads, Nq, Nk, 64
     a.scale = float(scale)
+    a.o_is_f32 = int(o.dtype == torch.float32)
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_attn_bwd(C.byref(a), _stream()), "pm_attn_bwd")
     _prof_end(t0, ("attention_bwd", B, heads, Nq, Nk), 3)

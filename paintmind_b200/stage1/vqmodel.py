@@ -2,8 +2,10 @@
 
 Same attributes (encoder, decoder, quantize, prev_quant, post_quant), same methods and return
 conventions, identical state_dict keys (222 tensors); the arithmetic runs in
-hand-written sm_100a kernels through engine.Stage1Engine.  Inference only: outputs carry no
-autograd graph."""
+hand-written sm_100a kernels through engine.Stage1Engine.  encode / decode / decode_from_indice are
+inference entry points (no autograd graph, like the reference's frozen tokenizer, generate.py:55-56);
+forward(img) — the call VQGANTrainer differentiates (utils/trainer.py:205-217) — carries gradients for
+every parameter when autograd is enabled (train.py: one autograd.Function over the backward kernels)."""
 from __future__ import annotations
 
 import torch
@@ -53,8 +55,13 @@ class VQModel(nn.Module):
         """[B,N,32] -> image [B,3,H,W] clamped to [-1,1] — vqmodel.py:27-30."""
         return _as_autocast(self.engine().decode(x))
 
-    @torch.no_grad()
     def forward(self, img):
+        """(rec, codebook loss) — vqmodel.py:32-36.  With autograd enabled and trainable parameters this is the
+        generator training step: both outputs are differentiable w.r.t. every parameter."""
+        if torch.is_grad_enabled() and img.shape[0] > 0 and any(p.requires_grad for p in self.parameters()):
+            from ..train import vqgan_forward_with_grad
+            rec, loss = vqgan_forward_with_grad(self, img)
+            return _as_autocast(rec), loss
         z, loss, _ = self.encode(img)
         return self.decode(z), loss
 
@@ -87,6 +94,12 @@ class VQModel(nn.Module):
         return self.engine().decode_from_indice(indice, pixels=True)
 
     # -- engine ------------------------------------------------------------------------------
+    def train_engine(self):
+        if self.__dict__.get("_train_engine") is None:
+            from ..train import Stage1TrainEngine
+            object.__setattr__(self, "_train_engine", Stage1TrainEngine(self))
+        return self._train_engine
+
     def engine(self):
         if self._engine is None:
             from ..engine import Stage1Engine
