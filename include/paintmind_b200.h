@@ -109,8 +109,9 @@ typedef struct pm_attn_args {
   int64_t bsq, bsk, bsv, bso;
   int32_t B, H, Nq, Nk, head_dim; /* head_dim must be 64 */
   float scale;                     /* dim_head ** -0.5 (attention.py:31) */
-  float* lse;                      /* optional out [B, H, Nq] fp32: log2-sum-exp2 of the scaled score rows, kept by a
+  float* lse;                      /* optional out [B, H, lse_ld] fp32: log2-sum-exp2 of the scaled score rows, kept by a
                                       training forward for pm_attn_bwd; NULL for inference */
+  int64_t lse_ld;                  /* row pitch of lse (0 = Nq); pm_attn_bwd wants Nq rounded up to a multiple of 128 */
   float* o32;                      /* optional out: fp32 copy of O, [B, Nq, ldo32] dense over the batch (training forward: */
   int64_t ldo32;                   /* keeps delta = rowsum(dO * O) of the backward free of O's bf16 rounding); else NULL   */
 } pm_attn_args;
@@ -236,8 +237,7 @@ int pm_ce_label_smooth(const float* logits, int64_t ld, int32_t M, int32_t V, co
  *   pm_swiglu_bwd       : hidden = silu(x1) * x2 backward (mlp.py:29-30) on the tile-interleaved x12 the packed w12
  *                         projection produces; also re-materialises `h` (operand of the w3 weight gradient).
  *   pm_attn_bwd         : backward of softmax(scale Q K^T) V (attention.py:52-57): dq, dk, dv from q, k, v, o, d_o and
- *                         the forward's lse.  delta: [B, H, Nq] fp32 scratch.  Nq, Nk multiples of 128 (self-attention
- *                         of the tokenizer: 1024).
+ *                         the forward's lse.  delta: [B, H, lse_ld] fp32 scratch.  Ragged token counts are masked.
  *   pm_vq_bwd           : VectorQuantizer backward (quantize.py:19,29-36): straight-through estimator + both loss
  *                         terms; dz fp32 [M, 32], dz_split bf16 [M, 64] = [hi | lo], dE[n_e, 32] += (fp32 atomics).
  *                         d_out: gradient of the returned z_q (may be NULL), d_loss: device scalar (may be NULL).
@@ -250,8 +250,8 @@ typedef struct pm_attn_bwd_args {
   const void* v;
   const void* o;      /* forward output: bf16, or the fp32 copy (o32 of pm_attn_fwd) when o_is_f32 */
   const void* d_o;    /* gradient of o */
-  const float* lse;   /* [B, H, Nq] from pm_attn_fwd */
-  float* delta;       /* [B, H, Nq] scratch */
+  const float* lse;   /* [B, H, lse_ld] from pm_attn_fwd */
+  float* delta;       /* [B, H, lse_ld] scratch */
   void* dq;
   void* dk;
   void* dv;
@@ -260,6 +260,7 @@ typedef struct pm_attn_bwd_args {
   int32_t B, H, Nq, Nk, head_dim;
   float scale;
   int32_t o_is_f32;
+  int64_t lse_ld;     /* row pitch of lse / delta: Nq rounded up to a multiple of 128 */
 } pm_attn_bwd_args;
 
 int pm_attn_bwd(const pm_attn_bwd_args* args, void* stream);

@@ -394,7 +394,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       if (p.lse != nullptr) {
         // training forward: base-2 log-sum-exp of the scaled score row, consumed by pm_attn_bwd
         const int qrow = it.qb * 2 * AT_BM + t * AT_BM + row_in_tile;
-        if (qrow < p.Nq) p.lse[(static_cast<size_t>(it.b) * p.H + it.h) * p.Nq + qrow] = m_used + log2f(l_sum);
+        if (qrow < p.Nq) p.lse[(static_cast<size_t>(it.b) * p.H + it.h) * p.lse_ld + qrow] = m_used + log2f(l_sum);
       }
       uint32_t r0[32], r1[32];
       tmem_ld_x32(tO, r0);

@@ -5,6 +5,7 @@
 // row log-sum-exp (base 2, `lse`) and delta = rowsum(dO ⊙ O):
 //     dV = P^T dO          dS = P ⊙ (dO V^T - delta) * scale          dQ = dS K          dK = dS^T Q
 // Two launches of one kernel template, no atomics, deterministic:
+// Token counts need not be multiples of 128: TMA zero-fills / clips the ragged tiles and the tail columns are masked.
 //   DKV = false : CTA = (128-query tile, head, batch), loops over key tiles.   rows = queries, columns = keys
 //                 S' = Q K_j^T,  dP' = dO V_j^T,  dQ += dS' K_j
 //   DKV = true  : CTA = (128-key tile, head, batch), loops over query tiles.  rows = keys, columns = queries
@@ -49,8 +50,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int T = (DKV ? p.Nq : p.Nk) / AB_T;               // column tiles to walk
-  const size_t vec_base = (static_cast<size_t>(b) * p.H + h) * p.Nq;     // lse / delta are per query
+  const int n_cols = DKV ? p.Nq : p.Nk;
+  const int T = (n_cols + AB_T - 1) / AB_T;               // column tiles to walk
+  const size_t vec_base = (static_cast<size_t>(b) * p.H + h) * p.lse_ld; // lse / delta are per query, rows padded to 128
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmR1); tma_prefetch_desc(&tmR2); tma_prefetch_desc(&tmC1); tma_prefetch_desc(&tmC2);
@@ -140,7 +142,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float c = p.scale_log2, sc = p.scale;
     float lse_row = 0.f, dl_row = 0.f;
-    if (!DKV) {
+    if (!DKV && rt * AB_T + row_in_tile < p.Nq) {
       lse_row = p.lse[vec_base + rt * AB_T + row_in_tile];
       dl_row = p.delta[vec_base + rt * AB_T + row_in_tile];
     }
@@ -148,6 +150,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       const int st = t % AB_NST;
       const float* lse_s = reinterpret_cast<const float*>(smem_raw + (sVec + st * 1024 - raw_a));
       const float* dl_s = lse_s + 128;
+      const int valid = n_cols - t * AB_T;                    // < 128 on a ragged last column tile (TMA zero-filled it)
       mbar_wait_a(s_full, t & 1);
       tc_fence_after();
       if (DKV) mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);     // this thread reads the TMA-written (lse, delta) vectors itself
@@ -166,10 +169,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             const float2 dv = *reinterpret_cast<const float2*>(dl_s + ch * 32 + e);
             l0 = lv.x; l1 = lv.y; d0 = dv.x; d1 = dv.y;
           }
-          const float p0 = ab_ex2(fmaf(__uint_as_float(s[e]), c, -l0));
-          const float p1 = ab_ex2(fmaf(__uint_as_float(s[e + 1]), c, -l1));
-          const float g0 = p0 * (__uint_as_float(dp[e]) - d0) * sc;
-          const float g1 = p1 * (__uint_as_float(dp[e + 1]) - d1) * sc;
+          float p0 = ab_ex2(fmaf(__uint_as_float(s[e]), c, -l0));
+          float p1 = ab_ex2(fmaf(__uint_as_float(s[e + 1]), c, -l1));
+          float g0 = p0 * (__uint_as_float(dp[e]) - d0) * sc;
+          float g1 = p1 * (__uint_as_float(dp[e + 1]) - d1) * sc;
+          if (valid < AB_T) {                                  // columns past the end contribute nothing
+            if (ch * 32 + e >= valid) p0 = 0.f, g0 = 0.f;
+            if (ch * 32 + e + 1 >= valid) p1 = 0.f, g1 = 0.f;
+          }
           pk[e >> 1] = pack_bf16x2(p0, p1);
           dk[e >> 1] = pack_bf16x2(g0, g1);
         }
@@ -240,7 +247,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream) {
   if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.dO == nullptr || p.lse == nullptr || p.delta == nullptr) return PM_ERR_INVALID;
   if (p.dq == nullptr || p.dk == nullptr || p.dv == nullptr) return PM_ERR_INVALID;
-  if (p.B <= 0 || p.H <= 0 || p.Nq <= 0 || p.Nk <= 0 || (p.Nq % AB_T) != 0 || (p.Nk % AB_T) != 0 || p.head_dim != AB_D) return PM_ERR_INVALID;
+  if (p.B <= 0 || p.H <= 0 || p.Nq <= 0 || p.Nk <= 0 || p.head_dim != AB_D) return PM_ERR_INVALID;
+  if (p.lse_ld < (p.Nq + AB_T - 1) / AB_T * AB_T || (p.lse_ld % 4) != 0) return PM_ERR_INVALID;     // whole 512-byte vector tiles are copied
   CUtensorMap tQ, tK, tV, tDO, tDQ, tDK, tDV;
   int rc;
   const uint64_t inner = static_cast<uint64_t>(p.H) * AB_D;
@@ -255,10 +263,10 @@ int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream) {
   if ((rc = pm_ensure_dyn_smem(attn_bwd_kernel<false>, AB_SMEM, attr_a)) != 0) return rc;
   if ((rc = pm_ensure_dyn_smem(attn_bwd_kernel<true>, AB_SMEM, attr_b)) != 0) return rc;
   // dK / dV: rows = keys (R1 = K, R2 = V), columns = queries (C1 = Q, C2 = dO); acc1 = dS' Q = dK, acc2 = P' dO = dV
-  attn_bwd_kernel<true><<<dim3(p.Nk / AB_T, p.H, p.B), AB_THREADS, AB_SMEM, stream>>>(tK, tV, tQ, tDO, tDK, tDV, p);
+  attn_bwd_kernel<true><<<dim3((p.Nk + AB_T - 1) / AB_T, p.H, p.B), AB_THREADS, AB_SMEM, stream>>>(tK, tV, tQ, tDO, tDK, tDV, p);
   if ((rc = static_cast<int>(cudaGetLastError())) != 0) return rc;
   // dQ: rows = queries (R1 = Q, R2 = dO), columns = keys (C1 = K, C2 = V); acc1 = dS' K = dQ
-  attn_bwd_kernel<false><<<dim3(p.Nq / AB_T, p.H, p.B), AB_THREADS, AB_SMEM, stream>>>(tQ, tDO, tK, tV, tDQ, tDQ, p);
+  attn_bwd_kernel<false><<<dim3((p.Nq + AB_T - 1) / AB_T, p.H, p.B), AB_THREADS, AB_SMEM, stream>>>(tQ, tDO, tK, tV, tDQ, tDQ, p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -41,6 +41,7 @@ struct AttnParams {
   int B, H, Nq, Nk, head_dim;
   float scale_log2;                // softmax scale * log2(e)
   float* lse;                      // optional [B, H, Nq] fp32 out: base-2 log-sum-exp of the scaled scores (training forward)
+  int64_t lse_ld;                  // row pitch of lse per (batch, head): >= Nq (pm_attn_bwd wants it rounded up to 128)
   float* o32;                      // optional [B, Nq, ldo32] fp32 copy of O (training forward; feeds delta of the backward)
   int64_t ldo32;
 };
@@ -53,8 +54,9 @@ struct AttnBwdParams {
   void* dq;
   void* dk;
   void* dv;
-  const float* lse;                // [B, H, Nq] from the forward
-  const float* delta;              // [B, H, Nq] rowsum(dO * O)
+  const float* lse;                // [B, H, lse_ld] from the forward
+  const float* delta;              // [B, H, lse_ld] rowsum(dO * O)
+  int64_t lse_ld;                  // >= Nq rounded up to 128
   int64_t ldq, ldk, ldv, lddo, lddq, lddk, lddv;
   int64_t bsq, bsk, bsv, bsdo, bsdq, bsdk, bsdv;
   int B, H, Nq, Nk, head_dim;
@@ -133,7 +135,7 @@ int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, con
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
 int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream);
 int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H,
-                         int N, float* delta, cudaStream_t stream);
+                         int N, float* delta, int64_t delta_ld, cudaStream_t stream);
 int pm_wgrad_splits(int M, int N, int K);
 int pm_wgrad_launch(const WgradParams& p, cudaStream_t stream);
 int pm_colsum_rows(int M, int N);

@@ -295,7 +295,7 @@ def attention_train(q, k, v, o, heads, scale, lse, o32=None):
     args.bsq, args.bsk, args.bsv, args.bso = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
     args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
     args.scale = float(scale)
-    args.lse = _ptr(lse)
+    args.lse, args.lse_ld = _ptr(lse), lse.stride(1)
     if o32 is not None:
         if o32.dtype != torch.float32 or not o32.is_contiguous():
             raise RuntimeError("attention_train: o32 must be a contiguous fp32 [B, Nq, heads*64] tensor")
@@ -306,11 +306,19 @@ def attention_train(q, k, v, o, heads, scale, lse, o32=None):
     return o
 
 
+def lse_buffer(B, heads, Nq, device):
+    """[B, heads, Nq] fp32 view whose rows are padded to a multiple of 128 (attention_bwd copies whole 512-byte tiles)."""
+    pad = (Nq + 127) // 128 * 128
+    return torch.empty(B, heads, pad, device=device, dtype=torch.float32)[:, :, :Nq]
+
+
 def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, heads, scale):
     """dq, dk, dv of softmax(scale q k^T) v; all [B, N, >= heads*64] bf16 views with last stride 1."""
     _require_cuda(q, k, v, o, d_o, lse, dq, dk, dv)
     B, Nq, Nk = q.shape[0], q.shape[1], k.shape[1]
-    delta = _workspace("attn_delta", B * heads * Nq, q.device)
+    if lse.stride(1) % 128 != 0 or lse.stride(1) < Nq:
+        raise RuntimeError("attention_bwd: lse rows must be padded to a multiple of 128 (see lse_buffer)")
+    delta = _workspace("attn_delta", B * heads * lse.stride(1), q.device)
     a = _lib.AttnBwdArgs()
     a.q, a.k, a.v, a.o, a.d_o = _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(d_o)
     a.lse, a.delta, a.dq, a.dk, a.dv = _ptr(lse), _ptr(delta), _ptr(dq), _ptr(dk), _ptr(dv)
@@ -321,6 +329,7 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, heads, scale):
     a.B, a.H, a.Nq, a.Nk, a.head_dim = B, heads, Nq, Nk, 64
     a.scale = float(scale)
     a.o_is_f32 = int(o.dtype == torch.float32)
+    a.lse_ld = lse.stride(1)
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_attn_bwd(C.byref(a), _stream()), "pm_attn_bwd")
     _prof_end(t0, ("attention_bwd", B, heads, Nq, Nk), 3)

@@ -160,7 +160,7 @@ class Stage1TrainEngine:
         stats = ws.get("stats", (M, 2), torch.float32, dev)
         qkv = ws.get("qkv", (M, 3 * inner), bf, dev)
         ao = ws.get("ao", (M, inner), bf, dev)
-        lse = ws.get("lse", (B, H, N), torch.float32, dev)
+        lse = ws.get("lse", (B, H, (N + 127) // 128 * 128), torch.float32, dev)[:, :, :N]
         ao32 = ws.get("ao32", (B, N, inner), torch.float32, dev)
         x_mid = ws.get("x_mid", (M, D), bf, dev)
         x12 = ws.get("x12", (M, 2 * hp), bf, dev)

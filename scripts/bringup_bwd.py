@@ -137,12 +137,12 @@ if want("swiglu"):
 
 # --------------------------------------------------------------------------------------------- attention forward lse + backward
 if want("attn"):
-    for (B, H, N) in [(2, 8, 1024), (1, 2, 128), (3, 8, 256)]:
+    for (B, H, N) in [(2, 8, 1024), (1, 2, 128), (3, 8, 256), (2, 2, 64), (2, 3, 200)]:
         inner = H * 64
         qkv = rnd(B, N, 3 * inner, scale=1.0).to(torch.bfloat16)
         q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
         o = torch.empty(B, N, inner, device=dev, dtype=torch.bfloat16)
-        lse = torch.empty(B, H, N, device=dev)
+        lse = ops.lse_buffer(B, H, N, dev)
         scale = 0.125
         ops.attention_train(q, k, v, o, H, scale, lse)
         qr, kr, vr = [t.float().view(B, N, H, 64).permute(0, 2, 1, 3).contiguous().requires_grad_(True) for t in (q, k, v)]
@@ -154,6 +154,10 @@ if want("attn"):
         do = rnd(B, N, inner).to(torch.bfloat16)
         oref.backward(do.float().view(B, N, H, 64).permute(0, 2, 1, 3))
         dqkv = torch.zeros(B, N, 3 * inner, device=dev, dtype=torch.bfloat16)
+        if N == 256:
+            o32 = torch.empty(B, N, inner, device=dev)
+            ops.attention_train(q, k, v, o, H, scale, lse, o32)
+            report(f"attn fwd o32 B={B} H={H} N={N}", o32.view(B, N, H, 64).permute(0, 2, 1, 3), oref, 2e-2)
         ops.attention_bwd(q, k, v, o, do, lse, dqkv[..., :inner], dqkv[..., inner:2 * inner], dqkv[..., 2 * inner:], H, scale)
         torch.cuda.synchronize()
         for nm, got, ref in (("dq", dqkv[..., :inner], qr.grad), ("dk", dqkv[..., inner:2 * inner], kr.grad), ("dv", dqkv[..., 2 * inner:], vr.grad)):
@@ -163,7 +167,7 @@ if want("attn"):
         inner = 512
         qkv = rnd(B, N, 3 * inner).to(torch.bfloat16)
         q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
-        o = torch.empty(B, N, inner, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, H, N, device=dev)
+        o = torch.empty(B, N, inner, device=dev, dtype=torch.bfloat16); lse = ops.lse_buffer(B, H, N, dev)
         do = rnd(B, N, inner).to(torch.bfloat16); dqkv = torch.empty_like(qkv)
         ms = timeit(lambda: ops.attention_train(q, k, v, o, H, 0.125, lse))
         log(f"   attn fwd (+lse) B=256: {ms:.3f} ms  {4.0 * B * H * N * N * 64 / ms / 1e9:.0f} TFLOP/s")
