@@ -237,7 +237,7 @@ int pm_ce_label_smooth(const float* logits, int64_t ld, int32_t M, int32_t V, co
  *   pm_swiglu_bwd       : hidden = silu(x1) * x2 backward (mlp.py:29-30) on the tile-interleaved x12 the packed w12
  *                         projection produces; also re-materialises `h` (operand of the w3 weight gradient).
  *   pm_attn_bwd         : backward of softmax(scale Q K^T) V (attention.py:52-57): dq, dk, dv from q, k, v, o, d_o and
- *                         the forward's lse.  delta: [B, H, lse_ld] fp32 scratch.  Ragged token counts are masked.
+ *                         the forward's lse.  delta: [2, B, H, lse_ld] fp32 scratch.  Ragged token counts are masked.
  *   pm_vq_bwd           : VectorQuantizer backward (quantize.py:19,29-36): straight-through estimator + both loss
  *                         terms; dz fp32 [M, 32], dz_split bf16 [M, 64] = [hi | lo], dE[n_e, 32] += (fp32 atomics).
  *                         d_out: gradient of the returned z_q (may be NULL), d_loss: device scalar (may be NULL).
@@ -251,7 +251,7 @@ typedef struct pm_attn_bwd_args {
   const void* o;      /* forward output: bf16, or the fp32 copy (o32 of pm_attn_fwd) when o_is_f32 */
   const void* d_o;    /* gradient of o */
   const float* lse;   /* [B, H, lse_ld] from pm_attn_fwd */
-  float* delta;       /* [B, H, lse_ld] scratch */
+  float* delta;       /* [2, B, H, lse_ld] scratch (the row term -scale * rowsum(d_o * o), and -lse) */
   void* dq;
   void* dk;
   void* dv;
@@ -261,6 +261,7 @@ typedef struct pm_attn_bwd_args {
   float scale;
   int32_t o_is_f32;
   int64_t lse_ld;     /* row pitch of lse / delta: Nq rounded up to a multiple of 128 */
+  int64_t* debug;     /* optional [B * H * ceil(max(Nq, Nk) / 128), 8] int64 cycle counters of the last kernel (profiling aid) or NULL */
 } pm_attn_bwd_args;
 
 int pm_attn_bwd(const pm_attn_bwd_args* args, void* stream);

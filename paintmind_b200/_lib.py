@@ -49,7 +49,7 @@ class AttnBwdArgs(C.Structure):
         ("bsq", C.c_int64), ("bsk", C.c_int64), ("bsv", C.c_int64), ("bso", C.c_int64), ("bsdo", C.c_int64),
         ("bsdq", C.c_int64), ("bsdk", C.c_int64), ("bsdv", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("head_dim", C.c_int32),
-        ("scale", C.c_float), ("o_is_f32", C.c_int32), ("lse_ld", C.c_int64),
+        ("scale", C.c_float), ("o_is_f32", C.c_int32), ("lse_ld", C.c_int64), ("debug", C.c_void_p),
     ]
 
 

@@ -85,11 +85,16 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
 int pm_attn_bwd(const pm_attn_bwd_args* a, void* stream) {
   if (a == nullptr || a->o == nullptr || a->delta == nullptr) return PM_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = pm_attn_delta_launch(a->o, a->o_is_f32, a->ldo, a->bso, a->d_o, a->lddo, a->bsdo, a->B, a->H, a->Nq, a->delta, a->lse_ld, st);
+  if (a->lse == nullptr || a->B <= 0 || a->H <= 0 || a->lse_ld < a->Nq) return PM_ERR_INVALID;
+  float* nds = a->delta;
+  float* nlse = a->delta + static_cast<size_t>(a->B) * a->H * a->lse_ld;
+  int rc = pm_attn_delta_launch(a->o, a->o_is_f32, a->ldo, a->bso, a->d_o, a->lddo, a->bsdo, a->B, a->H, a->Nq, a->lse, a->scale, nds, nlse,
+                                a->lse_ld, st);
   if (rc != 0) return rc;
   AttnBwdParams p;
   p.q = a->q; p.k = a->k; p.v = a->v; p.dO = a->d_o; p.dq = a->dq; p.dk = a->dk; p.dv = a->dv;
-  p.lse = a->lse; p.delta = a->delta; p.lse_ld = a->lse_ld;
+  p.nlse = nlse; p.nds = nds; p.lse_ld = a->lse_ld;
+  p.debug = reinterpret_cast<long long*>(a->debug);
   p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.lddo = a->lddo; p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
   p.bsq = a->bsq; p.bsk = a->bsk; p.bsv = a->bsv; p.bsdo = a->bsdo; p.bsdq = a->bsdq; p.bsdk = a->bsdk; p.bsdv = a->bsdv;
   p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.head_dim = a->head_dim;

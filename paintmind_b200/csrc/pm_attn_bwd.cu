@@ -13,9 +13,10 @@
 // In both, the two score-shaped products are SS MMAs (both operands K-major, 128 x 128 x 64) into TMEM; 128 threads
 // (one per TMEM lane = row) turn them into P' and dS' (packed bf16, written back to TMEM), which then feed TS MMAs
 // (A from TMEM, B = the very same shared-memory tile re-read as an MN-major operand — no transposes anywhere).
-// TMEM (512 columns): S' [0,128) dP' [128,256) P' [256,320) dS' [320,384) acc1 [384,448) acc2 [448,512).
 #include "pm_common.cuh"
 #include "pm_kernels.h"
+
+#include <type_traits>
 
 namespace pm {
 
@@ -23,7 +24,7 @@ constexpr int AB_T = 128;                      // tile edge (rows and columns)
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;       // 16 KB
 constexpr int AB_NST = 3;                      // column-operand ring depth
-constexpr int AB_THREADS = 192;                // 4 compute warps, TMA warp, MMA warp
+constexpr int AB_THREADS = 320;                // 2 compute warpgroups (8 warps), TMA warp, MMA warp
 constexpr int AB_SMEM = 1024 + 2 * AB_TILE + AB_NST * 2 * AB_TILE + AB_NST * 1024 + 256;
 
 __device__ __forceinline__ float ab_ex2(float x) {
@@ -31,7 +32,17 @@ __device__ __forceinline__ float ab_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// (ex2.approx.f16x2 — two exponentials per instruction — was tried: ptxas splits it into two MUFU.EX2.F16 operations,
+//  no throughput gain on sm_100a, 3.27 ms against 2.96 ms.)
 
+// Work split inside a CTA: the two score-shaped products of a step are issued for the whole 128-column tile (measured on
+// B200, scripts/ubench/mma_rate.cu: one tcgen05.mma with M = 128 costs ~73 cycles (SS) / ~82 cycles (TS) whatever N <= 128
+// is, so instruction COUNT is what the tensor pipe is bound by and N = 128 is the efficient shape), then compute
+// warpgroup g (warps 4g .. 4g+3, one thread per row) turns columns [64g, 64g + 64) into P' / dS': two compute warps share
+// every SM sub-partition (one warp per scheduler cannot hide its own MUFU / TMEM latencies).  The accumulating TS MMAs of
+// step t are queued BEHIND the SS MMAs of step t + 1, so the exponentials of t + 1 run underneath them; P' / dS' of t + 1
+// wait in registers until those TS MMAs have read the previous ones.
+// TMEM: S' [0,128) dP' [128,256) P' [256,320) dS' [320,384) acc1 [384,448) acc2 [448,512).
 template <bool DKV>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
@@ -42,19 +53,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const uint32_t sR1 = (raw_a + 1023u) & ~1023u;
   const uint32_t sR2 = sR1 + AB_TILE;
   const uint32_t sC = sR2 + AB_TILE;                       // [NST][C1 16 KB | C2 16 KB]
-  const uint32_t sVec = sC + AB_NST * 2 * AB_TILE;         // [NST][lse 512 B | delta 512 B]
+  const uint32_t sVec = sC + AB_NST * 2 * AB_TILE;         // [NST][-lse 512 B | -scale*delta 512 B]
   const uint32_t bars = sVec + AB_NST * 1024;
   const uint32_t r_full = bars, c_full = bars + 8, c_empty = c_full + 8 * AB_NST, s_full = c_empty + 8 * AB_NST;
-  const uint32_t p_full = s_full + 8, acc_done = p_full + 8, tmem_slot_a = acc_done + 8;
+  const uint32_t p_full = s_full + 8, acc_done = p_full + 8, s_free = acc_done + 8, tmem_slot_a = s_free + 8;   // p_full / s_free count the 8 compute warps
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot_a - raw_a));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int n_cols = DKV ? p.Nq : p.Nk;
   const int T = (n_cols + AB_T - 1) / AB_T;               // column tiles to walk
-  const size_t vec_base = (static_cast<size_t>(b) * p.H + h) * p.lse_ld; // lse / delta are per query, rows padded to 128
+  const size_t vec_base = (static_cast<size_t>(b) * p.H + h) * p.lse_ld; // per-query vectors, rows padded to 128
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmR1); tma_prefetch_desc(&tmR2); tma_prefetch_desc(&tmC1); tma_prefetch_desc(&tmC2);
     tma_prefetch_desc(&tmO1);
     if (DKV) tma_prefetch_desc(&tmO2);
@@ -62,11 +73,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     init(r_full, 1);
     for (int i = 0; i < AB_NST; ++i) { init(c_full + 8 * i, 1); init(c_empty + 8 * i, 1); }
     init(s_full, 1);
-    init(p_full, 4);
+    init(p_full, 8);
     init(acc_done, 1);
+    init(s_free, 8);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -74,10 +86,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320;
   const uint32_t tA1 = tmem_base + 384, tA2 = tmem_base + 448;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================================== TMA producer ======================================
     if (lane == 0) {
       mbar_arrive_expect_tx_a(r_full, 2 * AB_TILE);
@@ -90,23 +101,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         tma_load_3d_a(sC + st * 2 * AB_TILE, &tmC1, c_full + 8 * st, h * AB_D, t * AB_T, b);
         tma_load_3d_a(sC + st * 2 * AB_TILE + AB_TILE, &tmC2, c_full + 8 * st, h * AB_D, t * AB_T, b);
         if (DKV) {
-          // the 128 per-query (lse, delta) values of this column tile
+          // the 128 per-query (-lse, -scale * delta) values of this column tile
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(sVec + st * 1024), "l"(reinterpret_cast<uint64_t>(p.lse + vec_base + t * AB_T)), "r"(512u), "r"(c_full + 8 * st)
+                       ::"r"(sVec + st * 1024), "l"(reinterpret_cast<uint64_t>(p.nlse + vec_base + t * AB_T)), "r"(512u), "r"(c_full + 8 * st)
                        : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(sVec + st * 1024 + 512), "l"(reinterpret_cast<uint64_t>(p.delta + vec_base + t * AB_T)), "r"(512u), "r"(c_full + 8 * st)
+                       ::"r"(sVec + st * 1024 + 512), "l"(reinterpret_cast<uint64_t>(p.nds + vec_base + t * AB_T)), "r"(512u), "r"(c_full + 8 * st)
                        : "memory");
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================================== MMA issuer ========================================
     if (lane == 0) {
-      constexpr uint32_t idesc_ss = umma_idesc_bf16(AB_T, AB_T, 0, 0);     // both K-major
+      constexpr uint32_t idesc_ss = umma_idesc_bf16(AB_T, AB_T, 0, 0);     // 128 x 128 x 16, both K-major
       constexpr uint32_t idesc_ts = umma_idesc_bf16(AB_T, AB_D, 0, 1);     // A from TMEM, B MN-major
       const uint64_t dr1 = umma_desc_sw128(sR1), dr2 = umma_desc_sw128(sR2);
+      const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320;
+      long long w_c = 0, w_p = 0;
+      const long long t_begin = clock64();
       mbar_wait_a(r_full, 0);
+      const long long t_r = clock64();
+      auto issue_ss = [&](int t) {
+        const int st = t % AB_NST;
+        long long t0 = clock64();
+        mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);
+        w_c += clock64() - t0;
+        tc_fence_after();
+        const uint64_t dc1 = umma_desc_sw128(sC + st * 2 * AB_TILE), dc2 = umma_desc_sw128(sC + st * 2 * AB_TILE + AB_TILE);
+#pragma unroll
+        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tS, dr1 + 2 * k, dc1 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tDP, dr2 + 2 * k, dc2 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+        umma_commit_a(s_full);
+      };
+      // acc1 (+)= dS' C1 (and acc2 (+)= P' C2): the column operands re-read as MN-major, 128 contraction rows
       auto issue_ts = [&](int t) {
         const int st = t % AB_NST;
         const uint64_t dc1 = umma_desc_sw128(sC + st * 2 * AB_TILE), dc2 = umma_desc_sw128(sC + st * 2 * AB_TILE + AB_TILE);
@@ -118,112 +147,130 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         umma_commit_a(acc_done);
         umma_commit_a(c_empty + 8 * st);
       };
+      issue_ss(0);
       for (int t = 0; t < T; ++t) {
-        const int st = t % AB_NST;
-        mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);
-        if (t > 0) mbar_wait_a(p_full, (t - 1) & 1);        // P'/dS'(t-1) written, S'/dP'(t-1) consumed
+        if (t + 1 < T) {
+          mbar_wait_a(s_free, t & 1);                // S'/dP'(t) sit in the compute threads' registers:
+          issue_ss(t + 1);                           //   the next step's scores run underneath this step's exponentials
+        }
+        const long long t0 = clock64();
+        mbar_wait_a(p_full, t & 1);                  // P'/dS'(t) written
+        w_p += clock64() - t0;
         tc_fence_after();
-        const uint64_t dc1 = umma_desc_sw128(sC + st * 2 * AB_TILE), dc2 = umma_desc_sw128(sC + st * 2 * AB_TILE + AB_TILE);
-#pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tS, dr1 + 2 * k, dc1 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tDP, dr2 + 2 * k, dc2 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
-        umma_commit_a(s_full);
-        if (t > 0) issue_ts(t - 1);
+        issue_ts(t);                                 // this step's accumulation runs underneath the next step's exponentials
       }
-      mbar_wait_a(p_full, (T - 1) & 1);
-      tc_fence_after();
-      issue_ts(T - 1);
+      if (p.debug != nullptr) {
+        long long* d = p.debug + 8 * ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        d[0] = t_r - t_begin; d[1] = w_c; d[2] = w_p; d[3] = clock64() - t_begin;
+      }
     }
   } else {
-    // ===================================== compute warps =====================================
-    const int q = warp;                                       // TMEM lane quarter
+    // ===================================== compute warpgroups ================================
+    const int g = warp >> 2;                                  // column half
+    const int q = warp & 3;                                   // TMEM lane quarter
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const float c = p.scale_log2, sc = p.scale;
-    float lse_row = 0.f, dl_row = 0.f;
+    const uint32_t tSg = tmem_base + g * 64 + lane_off, tDPg = tSg + 128;
+    const uint32_t tPg = tmem_base + 256 + g * 32 + lane_off, tDSg = tPg + 64;
+    const uint32_t b_s_full = s_full, b_p_full = p_full, b_acc_done = acc_done;
+    const float2 c2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
+    float2 nl_row = make_float2(0.f, 0.f), nd_row = make_float2(0.f, 0.f);
     if (!DKV && rt * AB_T + row_in_tile < p.Nq) {
-      lse_row = p.lse[vec_base + rt * AB_T + row_in_tile];
-      dl_row = p.delta[vec_base + rt * AB_T + row_in_tile];
+      const float a = p.nlse[vec_base + rt * AB_T + row_in_tile], d = p.nds[vec_base + rt * AB_T + row_in_tile];
+      nl_row = make_float2(a, a);
+      nd_row = make_float2(d, d);
     }
+    long long w_s = 0, w_a = 0;
+    const long long t_begin = clock64();
     for (int t = 0; t < T; ++t) {
       const int st = t % AB_NST;
-      const float* lse_s = reinterpret_cast<const float*>(smem_raw + (sVec + st * 1024 - raw_a));
-      const float* dl_s = lse_s + 128;
-      const int valid = n_cols - t * AB_T;                    // < 128 on a ragged last column tile (TMA zero-filled it)
-      mbar_wait_a(s_full, t & 1);
+      const float* nl_s = reinterpret_cast<const float*>(smem_raw + (sVec + st * 1024 - raw_a)) + g * 64;
+      const float* nd_s = nl_s + 128;
+      const int valid = n_cols - t * AB_T - g * 64;           // < 64 on a ragged last column tile (TMA zero-filled it)
+      long long t0 = clock64();
+      mbar_wait_a(b_s_full, t & 1);
+      w_s += clock64() - t0;
       tc_fence_after();
-      if (DKV) mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);     // this thread reads the TMA-written (lse, delta) vectors itself
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t s[32], dp[32];
-        tmem_ld_x32(tS + lane_off + ch * 32, s);
-        tmem_ld_x32(tDP + lane_off + ch * 32, dp);
-        tmem_ld_wait();
-        uint32_t pk[16], dk[16];
+      if (DKV) mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);     // this thread reads the TMA-written vectors itself
+      uint32_t pk[2][16], dk[2][16];
+      uint32_t s[2][32], dp[2][32];
+      tmem_ld_x32(tSg, s[0]);
+      tmem_ld_x32(tDPg, dp[0]);
+      tmem_ld_x32(tSg + 32, s[1]);
+      tmem_ld_x32(tDPg + 32, dp[1]);
+      tmem_ld_wait();
+      // both score tiles of this step are in registers: hand the TMEM columns back for the next step's SS MMAs
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(s_free);
+      // P' = exp2(s * scale * log2e - lse);  dS' = P' * (dP' - delta) * scale   (packed fp32 pairs around the two MUFU ops)
+      auto tile_math = [&](auto masked) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float l0 = lse_row, l1 = lse_row, d0 = dl_row, d1 = dl_row;
-          if (DKV) {
-            const float2 lv = *reinterpret_cast<const float2*>(lse_s + ch * 32 + e);
-            const float2 dv = *reinterpret_cast<const float2*>(dl_s + ch * 32 + e);
-            l0 = lv.x; l1 = lv.y; d0 = dv.x; d1 = dv.y;
+        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float2 nl = nl_row, nd = nd_row;
+            if (DKV) {
+              nl = *reinterpret_cast<const float2*>(nl_s + ch * 32 + e);
+              nd = *reinterpret_cast<const float2*>(nd_s + ch * 32 + e);
+            }
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(s[ch][e]), __uint_as_float(s[ch][e + 1])), c2, nl);
+            float2 pp = make_float2(ab_ex2(a.x), ab_ex2(a.y));
+            float2 gg = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(dp[ch][e]), __uint_as_float(dp[ch][e + 1])), sc2, nd));
+            if (decltype(masked)::value) {                      // ragged last tile: columns past the end contribute nothing
+              if (ch * 32 + e >= valid) pp.x = 0.f, gg.x = 0.f;
+              if (ch * 32 + e + 1 >= valid) pp.y = 0.f, gg.y = 0.f;
+            }
+            pk[ch][e >> 1] = pack_bf16x2(pp.x, pp.y);
+            dk[ch][e >> 1] = pack_bf16x2(gg.x, gg.y);
           }
-          float p0 = ab_ex2(fmaf(__uint_as_float(s[e]), c, -l0));
-          float p1 = ab_ex2(fmaf(__uint_as_float(s[e + 1]), c, -l1));
-          float g0 = p0 * (__uint_as_float(dp[e]) - d0) * sc;
-          float g1 = p1 * (__uint_as_float(dp[e + 1]) - d1) * sc;
-          if (valid < AB_T) {                                  // columns past the end contribute nothing
-            if (ch * 32 + e >= valid) p0 = 0.f, g0 = 0.f;
-            if (ch * 32 + e + 1 >= valid) p1 = 0.f, g1 = 0.f;
-          }
-          pk[e >> 1] = pack_bf16x2(p0, p1);
-          dk[e >> 1] = pack_bf16x2(g0, g1);
         }
-        if (ch == 0 && t > 0) {
-          // the TS MMAs of the previous step read P' / dS' until this fires
-          mbar_wait_a(acc_done, (t - 1) & 1);
-          tc_fence_after();
-        }
-        tmem_st_x16(tDS + lane_off + ch * 16, dk);
-        if (DKV) tmem_st_x16(tP + lane_off + ch * 16, pk);
+      };
+      if (valid < 64) tile_math(std::true_type{});
+      else tile_math(std::false_type{});
+      if (t > 0) {
+        // the TS MMAs of the previous step (queued behind this step's SS MMAs) read P' / dS' until this fires
+        t0 = clock64();
+        mbar_wait_a(b_acc_done, (t - 1) & 1);
+        w_a += clock64() - t0;
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        tmem_st_x16(tDSg + ch * 16, dk[ch]);
+        if (DKV) tmem_st_x16(tPg + ch * 16, pk[ch]);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(p_full);
+      if (lane == 0) mbar_arrive_a(b_p_full);
     }
+    const long long t_loop = clock64();
     // ---- epilogue: accumulators -> bf16 -> swizzled staging (the row-operand tiles are dead by now) -> TMA store ----
+    // DKV: warpgroup 0 drains acc1 (dK), warpgroup 1 acc2 (dV); dQ: each warpgroup drains 32 of acc1's 64 columns.
     mbar_wait_a(acc_done, (T - 1) & 1);
     tc_fence_after();
-#pragma unroll 1
-    for (int a = 0; a < (DKV ? 2 : 1); ++a) {
-      uint32_t r0[32], r1[32];
-      tmem_ld_x32((a == 0 ? tA1 : tA2) + lane_off, r0);
-      tmem_ld_x32((a == 0 ? tA1 : tA2) + lane_off + 32, r1);
-      tmem_ld_wait();
-      uint8_t* stg = smem_raw + ((a == 0 ? sR1 : sR2) - raw_a) + row_in_tile * 128;
+    {
+      uint32_t r0[32];
+      uint8_t* stg = smem_raw + ((DKV && g == 1 ? sR2 : sR1) - raw_a) + row_in_tile * 128;
 #pragma unroll
-      for (int jv = 0; jv < 4; ++jv) {
-        uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(r0[jv * 8 + 0]), __uint_as_float(r0[jv * 8 + 1]));
-        o.y = pack_bf16x2(__uint_as_float(r0[jv * 8 + 2]), __uint_as_float(r0[jv * 8 + 3]));
-        o.z = pack_bf16x2(__uint_as_float(r0[jv * 8 + 4]), __uint_as_float(r0[jv * 8 + 5]));
-        o.w = pack_bf16x2(__uint_as_float(r0[jv * 8 + 6]), __uint_as_float(r0[jv * 8 + 7]));
-        *reinterpret_cast<uint4*>(stg + ((jv ^ (row_in_tile & 7)) << 4)) = o;
-      }
+      for (int half = 0; half < (DKV ? 2 : 1); ++half) {
+        const int col0 = DKV ? half * 32 : g * 32;
+        tmem_ld_x32((DKV && g == 1 ? tA2 : tA1) + lane_off + col0, r0);
+        tmem_ld_wait();
 #pragma unroll
-      for (int jv = 0; jv < 4; ++jv) {
-        uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(r1[jv * 8 + 0]), __uint_as_float(r1[jv * 8 + 1]));
-        o.y = pack_bf16x2(__uint_as_float(r1[jv * 8 + 2]), __uint_as_float(r1[jv * 8 + 3]));
-        o.z = pack_bf16x2(__uint_as_float(r1[jv * 8 + 4]), __uint_as_float(r1[jv * 8 + 5]));
-        o.w = pack_bf16x2(__uint_as_float(r1[jv * 8 + 6]), __uint_as_float(r1[jv * 8 + 7]));
-        *reinterpret_cast<uint4*>(stg + (((4 + jv) ^ (row_in_tile & 7)) << 4)) = o;
+        for (int jv = 0; jv < 4; ++jv) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r0[jv * 8 + 0]), __uint_as_float(r0[jv * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(r0[jv * 8 + 2]), __uint_as_float(r0[jv * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(r0[jv * 8 + 4]), __uint_as_float(r0[jv * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(r0[jv * 8 + 6]), __uint_as_float(r0[jv * 8 + 7]));
+          *reinterpret_cast<uint4*>(stg + (((col0 / 8 + jv) ^ (row_in_tile & 7)) << 4)) = o;
+        }
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, 256);
     if (threadIdx.x == 0) {
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                    ::"l"(reinterpret_cast<uint64_t>(&tmO1)), "r"(sR1), "r"(h * AB_D), "r"(rt * AB_T), "r"(b) : "memory");
@@ -232,12 +279,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                      ::"l"(reinterpret_cast<uint64_t>(&tmO2)), "r"(sR2), "r"(h * AB_D), "r"(rt * AB_T), "r"(b) : "memory");
       tma_store_commit();
       tma_store_wait_all<0>();
+      if (p.debug != nullptr) {
+        long long* d = p.debug + 8 * ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        d[4] = w_s; d[5] = w_a; d[6] = t_loop - t_begin; d[7] = clock64() - t_loop;
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -245,7 +296,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 }
 
 int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream) {
-  if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.dO == nullptr || p.lse == nullptr || p.delta == nullptr) return PM_ERR_INVALID;
+  if (p.q == nullptr || p.k == nullptr || p.v == nullptr || p.dO == nullptr || p.nlse == nullptr || p.nds == nullptr) return PM_ERR_INVALID;
   if (p.dq == nullptr || p.dk == nullptr || p.dv == nullptr) return PM_ERR_INVALID;
   if (p.B <= 0 || p.H <= 0 || p.Nq <= 0 || p.Nk <= 0 || p.head_dim != AB_D) return PM_ERR_INVALID;
   if (p.lse_ld < (p.Nq + AB_T - 1) / AB_T * AB_T || (p.lse_ld % 4) != 0) return PM_ERR_INVALID;     // whole 512-byte vector tiles are copied

@@ -210,13 +210,15 @@ int pm_swiglu_bwd_launch(const void* x12, int64_t ld12, const void* dh, int64_t 
 }
 
 // ----------------------------------------------------------------------------------------------
-// delta[b, h, n] = sum_d dO[b, n, h*64 + d] * O[b, n, h*64 + d]   (the softmax-backward row term).
+// nds[b, h, n] = -scale * sum_d dO[b, n, h*64 + d] * O[b, n, h*64 + d]   (the softmax-backward row term, pre-scaled and
+// negated so that the attention backward kernel applies it with one packed FMA) and nlse = -lse.
 // One warp per token, 8 columns per lane per pass; a head = 8 consecutive lanes.
 // ----------------------------------------------------------------------------------------------
 template <bool O32>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const void* __restrict__ o_, int64_t ldo, int64_t bso, const __nv_bfloat16* __restrict__ dO, int64_t lddo,
-                  int64_t bsdo, int B, int H, int N, float* __restrict__ delta, int64_t delta_ld) {
+                  int64_t bsdo, int B, int H, int N, const float* __restrict__ lse, float scale, float* __restrict__ nds,
+                  float* __restrict__ nlse, int64_t delta_ld) {
   const long long tok = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tok >= static_cast<long long>(B) * N) return;
@@ -241,20 +243,24 @@ attn_delta_kernel(const void* __restrict__ o_, int64_t ldo, int64_t bso, const _
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if ((lane & 7) == 0 && c < H * 64) delta[(static_cast<size_t>(b) * H + (c >> 6)) * delta_ld + n] = s;
+    if ((lane & 7) == 0 && c < H * 64) {
+      const size_t at = (static_cast<size_t>(b) * H + (c >> 6)) * delta_ld + n;
+      nds[at] = -scale * s;
+      nlse[at] = -lse[at];
+    }
   }
 }
 
 int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H,
-                         int N, float* delta, int64_t delta_ld, cudaStream_t stream) {
-  if (o == nullptr || dO == nullptr || delta == nullptr || B <= 0 || H <= 0 || N <= 0) return PM_ERR_INVALID;
+                         int N, const float* lse, float scale, float* nds, float* nlse, int64_t delta_ld, cudaStream_t stream) {
+  if (o == nullptr || dO == nullptr || nds == nullptr || nlse == nullptr || lse == nullptr || B <= 0 || H <= 0 || N <= 0) return PM_ERR_INVALID;
   if ((ldo % 8) != 0 || (lddo % 8) != 0 || (bso % 8) != 0 || (bsdo % 8) != 0) return PM_ERR_INVALID;
   const long long threads = static_cast<long long>(B) * N * 32;
   const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
   if (o_is_f32)
-    attn_delta_kernel<true><<<blocks, 256, 0, stream>>>(o, ldo, bso, reinterpret_cast<const __nv_bfloat16*>(dO), lddo, bsdo, B, H, N, delta, delta_ld);
+    attn_delta_kernel<true><<<blocks, 256, 0, stream>>>(o, ldo, bso, reinterpret_cast<const __nv_bfloat16*>(dO), lddo, bsdo, B, H, N, lse, scale, nds, nlse, delta_ld);
   else
-    attn_delta_kernel<false><<<blocks, 256, 0, stream>>>(o, ldo, bso, reinterpret_cast<const __nv_bfloat16*>(dO), lddo, bsdo, B, H, N, delta, delta_ld);
+    attn_delta_kernel<false><<<blocks, 256, 0, stream>>>(o, ldo, bso, reinterpret_cast<const __nv_bfloat16*>(dO), lddo, bsdo, B, H, N, lse, scale, nds, nlse, delta_ld);
   return static_cast<int>(cudaGetLastError());
 }
 

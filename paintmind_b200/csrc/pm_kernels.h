@@ -54,9 +54,10 @@ struct AttnBwdParams {
   void* dq;
   void* dk;
   void* dv;
-  const float* lse;                // [B, H, lse_ld] from the forward
-  const float* delta;              // [B, H, lse_ld] rowsum(dO * O)
+  const float* nlse;               // [B, H, lse_ld]: -lse (lse from the forward, base 2)
+  const float* nds;                // [B, H, lse_ld]: -scale * rowsum(dO * O)
   int64_t lse_ld;                  // >= Nq rounded up to 128
+  long long* debug;                // optional [CTAs of the larger grid, 8] int64 cycle counters (profiling aid), or nullptr
   int64_t ldq, ldk, ldv, lddo, lddq, lddk, lddv;
   int64_t bsq, bsk, bsv, bsdo, bsdq, bsdk, bsdv;
   int B, H, Nq, Nk, head_dim;
@@ -135,7 +136,7 @@ int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, con
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
 int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream);
 int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H,
-                         int N, float* delta, int64_t delta_ld, cudaStream_t stream);
+                         int N, const float* lse, float scale, float* nds, float* nlse, int64_t delta_ld, cudaStream_t stream);
 int pm_wgrad_splits(int M, int N, int K);
 int pm_wgrad_launch(const WgradParams& p, cudaStream_t stream);
 int pm_colsum_rows(int M, int N);

@@ -312,13 +312,13 @@ def lse_buffer(B, heads, Nq, device):
     return torch.empty(B, heads, pad, device=device, dtype=torch.float32)[:, :, :Nq]
 
 
-def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, heads, scale):
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, heads, scale, debug=None):
     """dq, dk, dv of softmax(scale q k^T) v; all [B, N, >= heads*64] bf16 views with last stride 1."""
     _require_cuda(q, k, v, o, d_o, lse, dq, dk, dv)
     B, Nq, Nk = q.shape[0], q.shape[1], k.shape[1]
     if lse.stride(1) % 128 != 0 or lse.stride(1) < Nq:
         raise RuntimeError("attention_bwd: lse rows must be padded to a multiple of 128 (see lse_buffer)")
-    delta = _workspace("attn_delta", B * heads * lse.stride(1), q.device)
+    delta = _workspace("attn_delta", 2 * B * heads * lse.stride(1), q.device)
     a = _lib.AttnBwdArgs()
     a.q, a.k, a.v, a.o, a.d_o = _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(d_o)
     a.lse, a.delta, a.dq, a.dk, a.dv = _ptr(lse), _ptr(delta), _ptr(dq), _ptr(dk), _ptr(dv)
@@ -330,6 +330,7 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, heads, scale):
     a.scale = float(scale)
     a.o_is_f32 = int(o.dtype == torch.float32)
     a.lse_ld = lse.stride(1)
+    a.debug = _ptr(debug)
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_attn_bwd(C.byref(a), _stream()), "pm_attn_bwd")
     _prof_end(t0, ("attention_bwd", B, heads, Nq, Nk), 3)
