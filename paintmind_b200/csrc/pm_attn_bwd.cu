@@ -24,7 +24,13 @@ constexpr int AB_T = 128;                      // tile edge (rows and columns)
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;       // 16 KB
 constexpr int AB_NST = 3;                      // column-operand ring depth
-constexpr int AB_THREADS = 320;                // 2 compute warpgroups (8 warps), TMA warp, MMA warp
+#ifndef AB_EMU
+#define AB_EMU 0                               // of every 4 score pairs, this many take the FMA-pipe exp2 (pm_common.cuh)
+#endif
+constexpr int AB_NWG = 4;                      // compute warpgroups: each owns 128 / AB_NWG columns of every tile
+constexpr int AB_COLS = AB_T / AB_NWG;         // 32
+constexpr int AB_CW = 4 * AB_NWG;              // compute warps
+constexpr int AB_THREADS = 32 * (AB_CW + 2);   // compute warpgroups, TMA warp, MMA warp
 constexpr int AB_SMEM = 1024 + 2 * AB_TILE + AB_NST * 2 * AB_TILE + AB_NST * 1024 + 256;
 
 __device__ __forceinline__ float ab_ex2(float x) {
@@ -43,6 +49,8 @@ __device__ __forceinline__ float ab_ex2(float x) {
 // step t are queued BEHIND the SS MMAs of step t + 1, so the exponentials of t + 1 run underneath them; P' / dS' of t + 1
 // wait in registers until those TS MMAs have read the previous ones.
 // TMEM: S' [0,128) dP' [128,256) P' [256,320) dS' [320,384) acc1 [384,448) acc2 [448,512).
+static_assert(AB_COLS == 32, "the compute loop is written for 32-column slices");
+
 template <bool DKV>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
@@ -65,7 +73,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const int T = (n_cols + AB_T - 1) / AB_T;               // column tiles to walk
   const size_t vec_base = (static_cast<size_t>(b) * p.H + h) * p.lse_ld; // per-query vectors, rows padded to 128
 
-  if (warp == 8 && lane == 0) {
+  if (warp == AB_CW && lane == 0) {
     tma_prefetch_desc(&tmR1); tma_prefetch_desc(&tmR2); tma_prefetch_desc(&tmC1); tma_prefetch_desc(&tmC2);
     tma_prefetch_desc(&tmO1);
     if (DKV) tma_prefetch_desc(&tmO2);
@@ -73,12 +81,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     init(r_full, 1);
     for (int i = 0; i < AB_NST; ++i) { init(c_full + 8 * i, 1); init(c_empty + 8 * i, 1); }
     init(s_full, 1);
-    init(p_full, 8);
+    init(p_full, AB_CW);
     init(acc_done, 1);
-    init(s_free, 8);
+    init(s_free, AB_CW);
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == AB_CW + 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -88,7 +96,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tA1 = tmem_base + 384, tA2 = tmem_base + 448;
 
-  if (warp == 8) {
+  if (warp == AB_CW) {
     // ===================================== TMA producer ======================================
     if (lane == 0) {
       mbar_arrive_expect_tx_a(r_full, 2 * AB_TILE);
@@ -111,7 +119,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == AB_CW + 1) {
     // ===================================== MMA issuer ========================================
     if (lane == 0) {
       constexpr uint32_t idesc_ss = umma_idesc_bf16(AB_T, AB_T, 0, 0);     // 128 x 128 x 16, both K-major
@@ -166,12 +174,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     }
   } else {
     // ===================================== compute warpgroups ================================
-    const int g = warp >> 2;                                  // column half
+    const int g = warp >> 2;                                  // column slice
     const int q = warp & 3;                                   // TMEM lane quarter
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tSg = tmem_base + g * 64 + lane_off, tDPg = tSg + 128;
-    const uint32_t tPg = tmem_base + 256 + g * 32 + lane_off, tDSg = tPg + 64;
+    const uint32_t tSg = tmem_base + g * AB_COLS + lane_off, tDPg = tSg + 128;
+    const uint32_t tPg = tmem_base + 256 + g * (AB_COLS / 2) + lane_off, tDSg = tPg + 64;
     const uint32_t b_s_full = s_full, b_p_full = p_full, b_acc_done = acc_done;
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
     float2 nl_row = make_float2(0.f, 0.f), nd_row = make_float2(0.f, 0.f);
@@ -180,54 +188,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       nl_row = make_float2(a, a);
       nd_row = make_float2(d, d);
     }
-    long long w_s = 0, w_a = 0;
+    long long w_s = 0, w_a = 0, c_ld = 0, c_math = 0, c_st = 0;
     const long long t_begin = clock64();
     for (int t = 0; t < T; ++t) {
       const int st = t % AB_NST;
-      const float* nl_s = reinterpret_cast<const float*>(smem_raw + (sVec + st * 1024 - raw_a)) + g * 64;
+      const float* nl_s = reinterpret_cast<const float*>(smem_raw + (sVec + st * 1024 - raw_a)) + g * AB_COLS;
       const float* nd_s = nl_s + 128;
-      const int valid = n_cols - t * AB_T - g * 64;           // < 64 on a ragged last column tile (TMA zero-filled it)
+      const int valid = n_cols - t * AB_T - g * AB_COLS;      // < 32 on a ragged last column tile (TMA zero-filled it)
       long long t0 = clock64();
       mbar_wait_a(b_s_full, t & 1);
       w_s += clock64() - t0;
       tc_fence_after();
       if (DKV) mbar_wait_a(c_full + 8 * st, (t / AB_NST) & 1);     // this thread reads the TMA-written vectors itself
-      uint32_t pk[2][16], dk[2][16];
-      uint32_t s[2][32], dp[2][32];
-      tmem_ld_x32(tSg, s[0]);
-      tmem_ld_x32(tDPg, dp[0]);
-      tmem_ld_x32(tSg + 32, s[1]);
-      tmem_ld_x32(tDPg + 32, dp[1]);
+      uint32_t pk[16], dk[16];
+      uint32_t s[32], dp[32];
+      t0 = clock64();
+      tmem_ld_x32(tSg, s);
+      tmem_ld_x32(tDPg, dp);
       tmem_ld_wait();
-      // both score tiles of this step are in registers: hand the TMEM columns back for the next step's SS MMAs
+      c_ld += clock64() - t0;
+      // both score slices of this step are in registers: hand the TMEM columns back for the next step's SS MMAs
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(s_free);
       // P' = exp2(s * scale * log2e - lse);  dS' = P' * (dP' - delta) * scale   (packed fp32 pairs around the two MUFU ops)
       auto tile_math = [&](auto masked) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float2 nl = nl_row, nd = nd_row;
-            if (DKV) {
-              nl = *reinterpret_cast<const float2*>(nl_s + ch * 32 + e);
-              nd = *reinterpret_cast<const float2*>(nd_s + ch * 32 + e);
-            }
-            const float2 a = __ffma2_rn(make_float2(__uint_as_float(s[ch][e]), __uint_as_float(s[ch][e + 1])), c2, nl);
-            float2 pp = make_float2(ab_ex2(a.x), ab_ex2(a.y));
-            float2 gg = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(dp[ch][e]), __uint_as_float(dp[ch][e + 1])), sc2, nd));
-            if (decltype(masked)::value) {                      // ragged last tile: columns past the end contribute nothing
-              if (ch * 32 + e >= valid) pp.x = 0.f, gg.x = 0.f;
-              if (ch * 32 + e + 1 >= valid) pp.y = 0.f, gg.y = 0.f;
-            }
-            pk[ch][e >> 1] = pack_bf16x2(pp.x, pp.y);
-            dk[ch][e >> 1] = pack_bf16x2(gg.x, gg.y);
+        for (int e = 0; e < 32; e += 2) {
+          float2 nl = nl_row, nd = nd_row;
+          if (DKV) {
+            nl = *reinterpret_cast<const float2*>(nl_s + e);
+            nd = *reinterpret_cast<const float2*>(nd_s + e);
           }
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), c2, nl);
+          float2 pp = (((e >> 1) & 3) < AB_EMU) ? exp2_poly2(a) : make_float2(ab_ex2(a.x), ab_ex2(a.y));
+          float2 gg = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), sc2, nd));
+          if (decltype(masked)::value) {                      // ragged last tile: columns past the end contribute nothing
+            if (e >= valid) pp.x = 0.f, gg.x = 0.f;
+            if (e + 1 >= valid) pp.y = 0.f, gg.y = 0.f;
+          }
+          pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
+          dk[e >> 1] = pack_bf16x2(gg.x, gg.y);
         }
       };
-      if (valid < 64) tile_math(std::true_type{});
+      t0 = clock64();
+      if (valid < AB_COLS) tile_math(std::true_type{});
       else tile_math(std::false_type{});
+      c_math += clock64() - t0;
       if (t > 0) {
         // the TS MMAs of the previous step (queued behind this step's SS MMAs) read P' / dS' until this fires
         t0 = clock64();
@@ -235,42 +242,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         w_a += clock64() - t0;
         tc_fence_after();
       }
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_st_x16(tDSg + ch * 16, dk[ch]);
-        if (DKV) tmem_st_x16(tPg + ch * 16, pk[ch]);
-      }
+      t0 = clock64();
+      tmem_st_x16(tDSg, dk);
+      if (DKV) tmem_st_x16(tPg, pk);
       tmem_st_wait();
+      c_st += clock64() - t0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(b_p_full);
     }
     const long long t_loop = clock64();
     // ---- epilogue: accumulators -> bf16 -> swizzled staging (the row-operand tiles are dead by now) -> TMA store ----
-    // DKV: warpgroup 0 drains acc1 (dK), warpgroup 1 acc2 (dV); dQ: each warpgroup drains 32 of acc1's 64 columns.
+    // DKV: warpgroups 0 / 1 drain the two 32-column halves of acc1 (dK), warpgroups 2 / 3 those of acc2 (dV);
+    // dQ: warpgroups 0 / 1 drain acc1.
     mbar_wait_a(acc_done, (T - 1) & 1);
     tc_fence_after();
-    {
+    if (DKV || g < 2) {
+      const bool second = DKV && g >= 2;
+      const int col0 = (g & 1) * 32;
       uint32_t r0[32];
-      uint8_t* stg = smem_raw + ((DKV && g == 1 ? sR2 : sR1) - raw_a) + row_in_tile * 128;
+      tmem_ld_x32((second ? tA2 : tA1) + lane_off + col0, r0);
+      tmem_ld_wait();
+      uint8_t* stg = smem_raw + ((second ? sR2 : sR1) - raw_a) + row_in_tile * 128;
 #pragma unroll
-      for (int half = 0; half < (DKV ? 2 : 1); ++half) {
-        const int col0 = DKV ? half * 32 : g * 32;
-        tmem_ld_x32((DKV && g == 1 ? tA2 : tA1) + lane_off + col0, r0);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jv = 0; jv < 4; ++jv) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r0[jv * 8 + 0]), __uint_as_float(r0[jv * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(r0[jv * 8 + 2]), __uint_as_float(r0[jv * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(r0[jv * 8 + 4]), __uint_as_float(r0[jv * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(r0[jv * 8 + 6]), __uint_as_float(r0[jv * 8 + 7]));
-          *reinterpret_cast<uint4*>(stg + (((col0 / 8 + jv) ^ (row_in_tile & 7)) << 4)) = o;
-        }
+      for (int jv = 0; jv < 4; ++jv) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r0[jv * 8 + 0]), __uint_as_float(r0[jv * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(r0[jv * 8 + 2]), __uint_as_float(r0[jv * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(r0[jv * 8 + 4]), __uint_as_float(r0[jv * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(r0[jv * 8 + 6]), __uint_as_float(r0[jv * 8 + 7]));
+        *reinterpret_cast<uint4*>(stg + (((col0 / 8 + jv) ^ (row_in_tile & 7)) << 4)) = o;
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(1, 256);
+    named_bar_sync(1, 32 * AB_CW);
     if (threadIdx.x == 0) {
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                    ::"l"(reinterpret_cast<uint64_t>(&tmO1)), "r"(sR1), "r"(h * AB_D), "r"(rt * AB_T), "r"(b) : "memory");
@@ -282,13 +287,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       if (p.debug != nullptr) {
         long long* d = p.debug + 8 * ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
         d[4] = w_s; d[5] = w_a; d[6] = t_loop - t_begin; d[7] = clock64() - t_loop;
+        d[1] = c_ld; d[2] = c_math; d[0] = c_st;      // (overwrite the MMA thread's wait counters: same CTA, written later)
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == AB_CW + 1) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

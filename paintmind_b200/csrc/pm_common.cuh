@@ -44,6 +44,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// exp2 on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, max relative error 7.5e-5 —
+// far below the bf16 rounding P undergoes).  MUFU.EX2 runs at 16/clk/SM and is the binding unit of the attention kernels
+// at head_dim 64, so a fixed fraction of the exponentials is computed here instead (packed f32x2 arithmetic).
+// Template parameter EMU of attn_kernel / constant AB_EMU of attn_bwd_kernel: of every 4 pairs of scores, this many take
+// the polynomial path.
+__device__ __forceinline__ float2 exp2_poly2(float2 a) {
+  a.x = fmaxf(a.x, -126.0f);
+  a.y = fmaxf(a.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);            // 1.5 * 2^23: rounds to nearest integer
+  const float2 t = __fadd2_rn(a, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), a);          // f in [-0.5, 0.5]
+  float2 pl = __ffma2_rn(make_float2(0.0551716685f, 0.0551716685f), f, make_float2(0.2426111251f, 0.2426111251f));
+  pl = __ffma2_rn(pl, f, make_float2(0.6932609677f, 0.6932609677f));
+  pl = __ffma2_rn(pl, f, make_float2(0.9999280572f, 0.9999280572f));
+  // scale by 2^n: n sits in the low mantissa bits of t, (bits << 23) lands it in the exponent field
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------

@@ -34,5 +34,6 @@ torch.cuda.synchronize()
 d = dbg.double().mean(0).tolist()
 T = N // 128
 print("last kernel (dQ), mean cycles per CTA:")
-print(f"  MMA thread : wait R {d[0]:.0f}  wait C (sum) {d[1]:.0f}  wait P (sum) {d[2]:.0f}  total {d[3]:.0f}  -> {d[3] / T:.0f} / iteration")
+print(f"  MMA thread : total {d[3]:.0f}  -> {d[3] / T:.0f} / iteration")
+print(f"  compute w0 per iteration: tcgen05.ld+wait {d[1] / T:.0f}  math {d[2] / T:.0f}  tcgen05.st+wait {d[0] / T:.0f}")
 print(f"  compute w0 : wait S (sum) {d[4]:.0f}  wait acc (sum) {d[5]:.0f}  loop {d[6]:.0f} ({d[6] / T:.0f} / iteration)  epilogue {d[7]:.0f}")
