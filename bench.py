@@ -357,6 +357,41 @@ def run_ours(args):
         e1.record(); torch.cuda.synchronize()
         vq_rate = 65536 * 20 / (e0.elapsed_time(e1) * 1e-3)
 
+    # secondary workload: the generator TRAINING step: VQModel.forward under autograd + backward of
+    # the path-only generator loss (utils/trainer.py:205-217 minus LPIPS / GAN), same batch per GPU.  Algorithmic FLOPs =
+    # 3 x the forward's (dgrad + wgrad per GEMM, 2.5 x for attention rounded up); recomputation is not counted.
+    train = None
+    if not args.no_train:
+        import torch.nn.functional as F
+        model.train()
+
+        def train_step():
+            model.zero_grad(set_to_none=True)
+            rec, closs = model(x_dev)
+            (closs + F.l1_loss(rec, x_dev) + F.mse_loss(rec, x_dev)).backward()
+
+        train_step()
+        barrier()
+        ops.LAUNCHES = 0
+        e0.record()
+        reps = 3
+        for _ in range(reps):
+            train_step()
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_train = float(tt.item())
+        gnorm = float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters())))
+        train = {"workload": "generator training step: VQModel.forward + backward of codebook + L1 + MSE loss, all 222 parameter gradients",
+                 "batch_per_gpu": B, "ms_per_step": ms_train, "images_per_s": B * world / (ms_train * 1e-3),
+                 "algorithmic_tflops_per_gpu": 3 * B * FLOP_PER_IMAGE / (ms_train * 1e-3) / 1e12,
+                 "gpu_launches_per_step": ops.LAUNCHES // reps, "grad_l2_norm": gnorm,
+                 "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+        model.zero_grad(set_to_none=True)
+        model.eval()
+
     # secondary workload: BASELINE configs[4] — MaskGIT iterative decode, 1024 tokens (reference-faithful),
     # 12 steps, random text embeddings, global batch 64 batch-sharded over the ranks, final image decoded once
     maskgit = None
@@ -416,7 +451,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_pixels": e2e_pixels,
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kernels, "vq_lookups_per_s": vq_rate, "maskgit": maskgit,
+            "kernels": kernels, "vq_lookups_per_s": vq_rate, "maskgit": maskgit, "train_step": train,
             "check": {"loss": global_loss, "codes_used": used_codes},
         }
         print(json.dumps(line), flush=True)
@@ -432,6 +467,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-maskgit", action="store_true", help="skip the secondary MaskGIT (BASELINE configs[4]) measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary generator-training-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
