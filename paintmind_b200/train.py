@@ -10,7 +10,10 @@ hand-written sm_100a kernels of libpaintmind_b200 (ops.py); torch only routes th
 Memory plan (M = B * 1024 tokens): the forward keeps ONE bf16 [M, D] checkpoint per transformer block (the block input)
 plus the few tensors at the path's joints (patch rows, pre-norm tokens, latents, indices, final decoder tokens, rec);
 the backward re-runs a block's forward from its checkpoint (qkv, attention + log-sum-exp, x_mid, x12) right before
-differentiating it.  16 checkpoints x 268 MB at B = 256 — 4.3 GB of the 180 GB.
+differentiating it.  16 checkpoints x 268 MB at B = 256 — 4.3 GB of the 180 GB.  When memory allows (`keep_attention`,
+decided per call from the free HBM) the forward also keeps each block's qkv, attention output (bf16 + fp32) and
+log-sum-exp — 1.6 GB per block at B = 256 — and the backward skips the attention recomputation (the most expensive
+part of it: 1.26 of 2.0 ms per block).
 
 Backward of one block (dgrad = pm_gemm_bf16 against the transposed weight, wgrad = pm_wgrad_bf16):
     dh   = dx W3                     dW3 = dx^T h        db3 = colsum(dx)
@@ -73,6 +76,7 @@ class Stage1TrainEngine:
         self.eng = model.engine()
         self._fp = None
         self.ws = self.eng.ws            # one activation workspace for forward and backward
+        self.keep_attention = None       # None = decide from free memory; True / False force the policy
 
     def _ensure_packed(self):
         self.eng._ensure_packed()
@@ -121,10 +125,11 @@ class Stage1TrainEngine:
         ops.gemm(patches, e.w_pe, x0, **e.enc_pos)
         ops.layernorm(x0, gamma=e.pre_g, beta=e.pre_b, y=x, stats=st.finished())
         sv["patches"], sv["x0"] = patches, x0
-        sv["enc_ckpt"] = []
+        keep = self._keep_policy(M, enc.dim, len(e.enc_blocks) + len(e.dec_blocks), dev)
+        sv["enc_ckpt"], sv["enc_attn"] = [], []
         for blk in e.enc_blocks:
             sv["enc_ckpt"].append(x.clone())
-            run_blocks([blk], x, st, B, N, ws)
+            sv["enc_attn"].append(self._block_forward(blk, x, st, B, N, keep))
         sv["x_enc"] = x.clone()
         z = torch.empty(M, m.quantize.e_dim, device=dev, dtype=torch.float32)
         ops.gemm(x, e.w_prev, z, bias=e.b_prev, out_mode=PM_OUT_F32, bn=32)
@@ -136,10 +141,10 @@ class Stage1TrainEngine:
         xd = ws.get("x", (M, Dd), torch.bfloat16, dev)
         st = _RowStats(ws, M, Dd, dev)
         ops.gemm(r["zq_split"], e.w_post, xd, bias=e.b_post, stats_out=st.produce(), **e.dec_pos)
-        sv["dec_ckpt"] = []
+        sv["dec_ckpt"], sv["dec_attn"] = [], []
         for blk in e.dec_blocks:
             sv["dec_ckpt"].append(xd.clone())
-            run_blocks([blk], xd, st, B, N, ws)
+            sv["dec_attn"].append(self._block_forward(blk, xd, st, B, N, keep))
         sv["x_dec"] = xd.clone()
         rec = torch.empty(B, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
         ops.gemm(xd, e.w_proj_chw, rec, bias=e.b_proj_chw, colsum=e.cs_proj_chw, out_mode=PM_OUT_UNPATCH, patch=8, channels=3,
@@ -147,8 +152,37 @@ class Stage1TrainEngine:
         sv["rec"] = rec
         return rec, loss, sv
 
+    def _keep_policy(self, M, D, n_blocks, dev):
+        if self.keep_attention is not None:
+            return bool(self.keep_attention)
+        per_block = M * D * (3 * 2 + 2 + 4) + M * 8 * 4            # qkv + ao (bf16) + ao (fp32) + lse, inner == D
+        free, _ = torch.cuda.mem_get_info(dev)
+        return n_blocks * per_block < 0.4 * free
+
+    def _block_forward(self, blk, x, st, B, N, keep):
+        """One pre-LN block in place on x (same kernels as engine.run_blocks).  keep=True: qkv / attention output /
+        log-sum-exp go to fresh tensors that are returned for the backward pass instead of the shared workspace."""
+        if not keep:
+            run_blocks([blk], x, st, B, N, self.eng.ws)
+            return None
+        M, D = x.shape
+        dev = x.device
+        inner, H = blk.inner, blk.heads
+        qkv = torch.empty(M, 3 * inner, device=dev, dtype=torch.bfloat16)
+        ao = torch.empty(M, inner, device=dev, dtype=torch.bfloat16)
+        ao32 = torch.empty(B, N, inner, device=dev, dtype=torch.float32)
+        lse = ops.lse_buffer(B, H, N, dev)
+        ops.gemm(x, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, **st.consume())
+        q3 = qkv.view(B, N, 3 * inner)
+        ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32)
+        ops.gemm(ao, blk.w_o, x, bias=blk.b_o, res=x, stats_out=st.produce())
+        h = self.eng.ws.get("h", (M, blk.hp), torch.bfloat16, dev)
+        ops.gemm(x, blk.w_12, h, bias=blk.b_12, colsum=blk.cs_12, swiglu=True, **st.consume())
+        ops.gemm(h, blk.w_3, x, bias=blk.b_3, res=x, stats_out=st.produce())
+        return (qkv, ao, ao32, lse)
+
     # ---------------------------------------------------------------------------------------- backward
-    def _block_backward(self, blk, bw, x_in, dx, B, N, grads, prefix):
+    def _block_backward(self, blk, bw, x_in, dx, B, N, grads, prefix, kept=None):
         """dx (bf16 [M, D], gradient of the block OUTPUT) is replaced by the gradient of the block INPUT; parameter
         gradients are written into `grads` under the reference names."""
         ws = self.ws
@@ -158,16 +192,20 @@ class Stage1TrainEngine:
         bf = torch.bfloat16
         # ---- recompute the block's forward from its checkpoint ----
         stats = ws.get("stats", (M, 2), torch.float32, dev)
-        qkv = ws.get("qkv", (M, 3 * inner), bf, dev)
-        ao = ws.get("ao", (M, inner), bf, dev)
-        lse = ws.get("lse", (B, H, (N + 127) // 128 * 128), torch.float32, dev)[:, :, :N]
-        ao32 = ws.get("ao32", (B, N, inner), torch.float32, dev)
         x_mid = ws.get("x_mid", (M, D), bf, dev)
         x12 = ws.get("x12", (M, 2 * hp), bf, dev)
-        ops.layernorm(x_in, stats=stats)
-        ops.gemm(x_in, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, stats=stats)
-        q3 = qkv.view(B, N, 3 * inner)
-        ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32)
+        if kept is not None:
+            qkv, ao, ao32, lse = kept
+            q3 = qkv.view(B, N, 3 * inner)
+        else:
+            qkv = ws.get("qkv", (M, 3 * inner), bf, dev)
+            ao = ws.get("ao", (M, inner), bf, dev)
+            lse = ws.get("lse", (B, H, (N + 127) // 128 * 128), torch.float32, dev)[:, :, :N]
+            ao32 = ws.get("ao32", (B, N, inner), torch.float32, dev)
+            ops.layernorm(x_in, stats=stats)
+            ops.gemm(x_in, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, stats=stats)
+            q3 = qkv.view(B, N, 3 * inner)
+            ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32)
         ops.gemm(ao, blk.w_o, x_mid, bias=blk.b_o, res=x_in)
         ops.layernorm(x_mid, stats=stats)
         ops.gemm(x_mid, blk.w_12, x12, bias=blk.b_12, colsum=blk.cs_12, stats=stats)          # plain store: gate | value tiles
@@ -263,7 +301,8 @@ class Stage1TrainEngine:
             # ---- decoder blocks, last to first ----
             for li in reversed(range(len(e.dec_blocks))):
                 self._block_backward(e.dec_blocks[li], self.dec_bwd[li], sv["dec_ckpt"][li], dx, B, N, grads,
-                                     f"decoder.transformer.layers.{li}.")
+                                     f"decoder.transformer.layers.{li}.", sv["dec_attn"][li])
+                sv["dec_ckpt"][li] = sv["dec_attn"][li] = None          # release as the backward pass retreats
             # ---- post_quant + decoder position embedding (vqmodel.py:28, layers.py:146) ----
             gpos = torch.empty(N * D, **f32)
             ops.colsum(dx.view(B, N * D), gpos)
@@ -296,7 +335,8 @@ class Stage1TrainEngine:
         # ---- encoder blocks ----
         for li in reversed(range(len(e.enc_blocks))):
             self._block_backward(e.enc_blocks[li], self.enc_bwd[li], sv["enc_ckpt"][li], dxe, B, N, grads,
-                                 f"encoder.transformer.layers.{li}.")
+                                 f"encoder.transformer.layers.{li}.", sv["enc_attn"][li])
+            sv["enc_ckpt"][li] = sv["enc_attn"][li] = None
         # ---- norm_pre, position embedding, patch embedding (layers.py:107-109) ----
         dx0 = ws.get("dn", (M, De), bf, dev)
         gbp = torch.empty(2, De, **f32)

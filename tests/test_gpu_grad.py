@@ -144,7 +144,7 @@ def test_unpatchify_bwd(ops):
     assert torch.equal(out, ref.bfloat16())
 
 
-def _model_and_grads(cfg_name, seed, batch):
+def _model_and_grads(cfg_name, seed, batch, keep=None):
     import paintmind_b200 as pm
     from paintmind_b200.config import ver2cfg
     from paintmind_b200.utils import synthetic
@@ -153,6 +153,7 @@ def _model_and_grads(cfg_name, seed, batch):
     model = pm.create_model(arch="vqgan", version=cfg_name, pretrained=False)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().train()
+    model.train_engine().keep_attention = keep       # None: decided from free memory; False: recompute attention in backward
     img = synthetic.make_images(batch, cfg["enc"]["image_size"], seed=seed + 200).cuda()
     rec, closs = model(img)
     assert rec.requires_grad and closs.requires_grad
@@ -163,10 +164,10 @@ def _model_and_grads(cfg_name, seed, batch):
     return cfg, sd, model, img, float(L.detach()), grads
 
 
-@pytest.mark.parametrize("cfg_name,seed,batch", [("vit-tiny-test", 7, 3), ("vit-s-vqgan", 0, 2)])
-def test_model_gradients_vs_oracle_autograd(cuda_device, cfg_name, seed, batch):
+@pytest.mark.parametrize("cfg_name,seed,batch,keep", [("vit-tiny-test", 7, 3, False), ("vit-s-vqgan", 0, 2, True), ("vit-tiny-test", 7, 3, True)])
+def test_model_gradients_vs_oracle_autograd(cuda_device, cfg_name, seed, batch, keep):
     from oracle import paintmind_oracle_torch as OT
-    cfg, sd, model, img, L, grads = _model_and_grads(cfg_name, seed, batch)
+    cfg, sd, model, img, L, grads = _model_and_grads(cfg_name, seed, batch, keep)
     with torch.no_grad():
         _, _, idx = model.encode(img)
     sdg = {k: v.cuda().clone().requires_grad_(True) for k, v in sd.items()}
