@@ -30,20 +30,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 // += gridDim.x * 8 and leaves its partial (dgamma | dbeta) in part[blockIdx.x, 2, D]; colreduce_kernel sums the blocks.
 // ----------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 2 ? 3 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfloat16* __restrict__ x, int64_t ldx,
               const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres, int64_t ldres,
               __nv_bfloat16* __restrict__ dx, int64_t lddx, int M, int D, float eps, float* __restrict__ part) {
   extern __shared__ float red[];                 // [8][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  float gm[NV][8], ag[NV][8], ab[NV][8];
+  float ag[NV][8], ab[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = i * 32 + lane;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      gm[i][k] = vi < nvec ? gamma[vi * 8 + k] : 0.f;
       ag[i][k] = 0.f;
       ab[i][k] = 0.f;
     }
@@ -81,13 +79,17 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfl
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (i * 32 + lane < nvec) {
+        // gamma is re-read per row (L1-resident, 2 x 16 B per lane): keeping it in registers cost an occupancy step
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 8 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float xh = (xv[i][k] - mu) * rstd;
           const float dnv = gv[i][k];
           ag[i][k] = fmaf(dnv, xh, ag[i][k]);
           ab[i][k] += dnv;
-          const float g = dnv * gm[i][k];
+          const float g = dnv * gm[k];
           xv[i][k] = xh;
           gv[i][k] = g;
           c1 += g;
@@ -135,16 +137,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfl
   }
 }
 
-__global__ void colreduce2_kernel(const float* __restrict__ partial, int R, int N, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  float s = 0.f;
-  for (int r = 0; r < R; ++r) s += partial[static_cast<size_t>(r) * N + c];
-  out[c] = s;
-}
-
 int pm_ln_bwd_blocks(int M) {
-  const int want = (M + 7) / 8, cap = 4 * pm_num_sms();
+  const int want = (M + 7) / 8, cap = 6 * pm_num_sms();
   return want < cap ? want : cap;
 }
 
@@ -162,8 +156,7 @@ int pm_ln_bwd_launch(const void* dn, int64_t lddn, const void* x, int64_t ldx, c
   if (D <= 256) ln_bwd_kernel<1><<<blocks, 256, smem, stream>>>(a, lddn, b, ldx, gamma, c, ldres, d, lddx, M, D, eps, part);
   else if (D <= 512) ln_bwd_kernel<2><<<blocks, 256, smem, stream>>>(a, lddn, b, ldx, gamma, c, ldres, d, lddx, M, D, eps, part);
   else ln_bwd_kernel<4><<<blocks, 256, smem, stream>>>(a, lddn, b, ldx, gamma, c, ldres, d, lddx, M, D, eps, part);
-  colreduce2_kernel<<<(2 * D + 255) / 256, 256, 0, stream>>>(part, blocks, 2 * D, dgamma_dbeta);
-  return static_cast<int>(cudaGetLastError());
+  return pm_colreduce_launch(part, blocks, 2 * D, dgamma_dbeta, 0, stream);
 }
 
 // ----------------------------------------------------------------------------------------------

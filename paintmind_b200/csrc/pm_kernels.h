@@ -140,6 +140,7 @@ int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, 
 int pm_wgrad_splits(int M, int N, int K);
 int pm_wgrad_launch(const WgradParams& p, cudaStream_t stream);
 int pm_colsum_rows(int M, int N);
+int pm_colreduce_launch(const float* partial, int R, int N, float* out, int accumulate, cudaStream_t stream);
 int pm_colsum_launch(const void* x, int64_t ld, int M, int N, float* partial, float* out, int accumulate, cudaStream_t stream);
 int pm_ln_bwd_blocks(int M);
 int pm_ln_bwd_launch(const void* dn, int64_t lddn, const void* x, int64_t ldx, const float* gamma, const void* dres,

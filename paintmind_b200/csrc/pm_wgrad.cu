@@ -238,13 +238,29 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N
   }
 }
 
-// out[c] (+)= sum_r partial[r, c]
-__global__ void colreduce_kernel(const float* __restrict__ partial, int R, int N, float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+// out[c] (+)= sum_r partial[r, c], fixed order: block = 32 columns x 32 row lanes (row lane y sums rows y, y + 32, ... and
+// the 32 lane sums are added in order) — one thread per column walking hundreds of partial rows was latency-bound
+// (~0.1 ms for a [592, 1024] partial, more than the pass that produced it).
+__global__ void __launch_bounds__(1024)
+colreduce_kernel(const float* __restrict__ partial, int R, int N, float* __restrict__ out, int accumulate) {
+  __shared__ float red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int r = 0; r < R; ++r) s += partial[static_cast<size_t>(r) * N + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < N)
+    for (int r = threadIdx.y; r < R; r += 32) s += partial[static_cast<size_t>(r) * N + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+int pm_colreduce_launch(const float* partial, int R, int N, float* out, int accumulate, cudaStream_t stream) {
+  colreduce_kernel<<<(N + 31) / 32, dim3(32, 32), 0, stream>>>(partial, R, N, out, accumulate);
+  return static_cast<int>(cudaGetLastError());
 }
 
 int pm_colsum_rows(int M, int N) {
@@ -263,8 +279,7 @@ int pm_colsum_launch(const void* x, int64_t ld, int M, int N, float* partial, fl
   const int rows_per = (M + R - 1) / R;
   dim3 grid((N + 255) / 256, R), block(32, 8);
   colsum_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, M, N, rows_per, partial);
-  colreduce_kernel<<<(N + 255) / 256, 256, 0, stream>>>(partial, R, N, out, accumulate);
-  return static_cast<int>(cudaGetLastError());
+  return pm_colreduce_launch(partial, R, N, out, accumulate, stream);
 }
 
 }  // namespace pm
