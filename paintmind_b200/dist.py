@@ -58,3 +58,33 @@ def tokenize_sharded(model, images_fn, total: int, batch: int, group=None):
     allreduce_usage(hist, sums, group)
     idx = torch.cat(out) if out else torch.empty(0, 0, dtype=torch.int64, device=dev)
     return idx, hist, global_loss(sums, model.quantize.beta)
+
+
+def allreduce_gradients(module, group=None, average: bool = True, bucket: torch.Tensor | None = None):
+    """Data-parallel generator training (the reference wraps its trainer in accelerate / DDP, utils/trainer.py:74-90,216):
+    every rank runs the training step on its own batch shard with replicated weights; the only exchange is ONE
+    all-reduce of the parameter gradients, flattened into a single fp32 bucket (208 MB for vit-s-vqgan: one NCCL call
+    over NVLink instead of 222 small ones), averaged over the ranks and scattered back into `.grad`.
+    Returns the bucket (pass it back in to reuse the allocation)."""
+    params = [p for p in module.parameters() if p.grad is not None]
+    if not params:
+        return bucket
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return bucket
+    n = sum(p.grad.numel() for p in params)
+    dev = params[0].grad.device
+    if bucket is None or bucket.numel() < n or bucket.device != dev:
+        bucket = torch.empty(n, device=dev, dtype=torch.float32)
+    flat = bucket[:n]
+    views, off = [], 0
+    for p in params:
+        k = p.grad.numel()
+        views.append(flat[off:off + k].view_as(p.grad))
+        off += k
+    torch._foreach_copy_(views, [p.grad for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.mul_(1.0 / world)
+    torch._foreach_copy_([p.grad for p in params], views)
+    return bucket

@@ -66,3 +66,46 @@ def test_allreduce_usage_world2_equals_single_process():
         assert torch.equal(hist, want_hist)                       # integer counts: bit-exact
         torch.testing.assert_close(sums, want_sums, atol=1e-12, rtol=1e-12)
         assert abs(pmdist.global_loss(sums) - 1.25 * float(want_sums[0] / want_sums[1])) < 1e-15
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.LayerNorm(7), torch.nn.Linear(7, 3))
+    net[2].bias.requires_grad_(False)                                       # a parameter without a gradient is skipped
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in net.parameters():
+        if p.requires_grad:
+            p.grad = torch.randn(p.shape, generator=g)
+    bucket = pmdist.allreduce_gradients(net)
+    bucket2 = pmdist.allreduce_gradients(net, bucket=bucket, average=False)  # second call reuses the bucket; SUM of the means
+    q.put((rank, [p.grad.tolist() for p in net.parameters() if p.grad is not None], bucket2.data_ptr() == bucket.data_ptr()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_world2():
+    """One flattened all-reduce averages every gradient over the ranks (data-parallel generator training)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shapes = [(7, 5), (7,), (7,), (7,), (3, 7)]
+    per_rank = []
+    for r in range(world):
+        g = torch.Generator().manual_seed(100 + r)
+        per_rank.append([torch.randn(s, generator=g) for s in shapes])
+    mean = [(a + b) / 2 for a, b in zip(*per_rank)]
+    for rank, grads, reused in outs:
+        assert reused
+        assert len(grads) == len(shapes)
+        for got, want in zip(grads, mean):
+            torch.testing.assert_close(torch.tensor(got), want * world, atol=1e-6, rtol=1e-6)   # mean, then summed again over 2 ranks
