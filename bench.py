@@ -189,10 +189,24 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to STDOUT: send its log to stderr so that stdout
-        # carries the one JSON line only
+        # stdout must carry the one JSON line only.  The GPU boxes export NCCL_DEBUG=VERSION and NCCL prints its version
+        # banner to STDOUT when the first communicator is created (NCCL_DEBUG_FILE does not catch it): lower the level and,
+        # belt and braces, point fd 1 at stderr while the communicator comes up (eagerly, because device_id is given).
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group(backend="nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend="nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     cfg = ver2cfg["vit-s-vqgan"]
     model = pm.create_model(arch="vqgan", version="vit-s-vqgan", pretrained=False)

@@ -29,7 +29,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # keep NCCL's banner off stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # the banner goes to stdout whatever NCCL_DEBUG_FILE says
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = ver2cfg["vit-s-vqgan"]
     model = pm.create_model(arch="vqgan", version="vit-s-vqgan", pretrained=False)
