@@ -219,7 +219,7 @@ class Stage1TrainEngine:
         f32 = dict(device=dev, dtype=torch.float32)
         b3 = torch.empty(D, **f32)
         ops.colsum(dx, b3)
-        ops.gemm(dx, bw.w_3_t, dh)
+        ops.gemm(dx, bw.w_3_t, dh, bn=256 if M >= 256 else 0)      # 1408 = 5.5 x 256: CTA pairs with a ragged last tile beat bn = 128
         ops.swiglu_bwd(x12, dh, h, d12)
         w3 = torch.empty(D, hp, **f32)
         ops.wgrad(dx, h, w3)
