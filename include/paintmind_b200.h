@@ -261,7 +261,7 @@ typedef struct pm_attn_bwd_args {
   float scale;
   int32_t o_is_f32;
   int64_t lse_ld;     /* row pitch of lse / delta: Nq rounded up to a multiple of 128 */
-  int64_t* debug;     /* optional [B * H * ceil(max(Nq, Nk) / 128), 8] int64 cycle counters of the last kernel (profiling aid) or NULL */
+  int64_t* debug;     /* optional [#SMs, 8] int64 cycle counters of the last kernel (profiling aid) or NULL */
 } pm_attn_bwd_args;
 
 int pm_attn_bwd(const pm_attn_bwd_args* args, void* stream);

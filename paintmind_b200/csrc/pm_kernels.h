@@ -57,7 +57,7 @@ struct AttnBwdParams {
   const float* nlse;               // [B, H, lse_ld]: -lse (lse from the forward, base 2)
   const float* nds;                // [B, H, lse_ld]: -scale * rowsum(dO * O)
   int64_t lse_ld;                  // >= Nq rounded up to 128
-  long long* debug;                // optional [CTAs of the larger grid, 8] int64 cycle counters (profiling aid), or nullptr
+  long long* debug;                // optional [#SMs, 8] int64 cycle counters of the last launch (profiling aid), or nullptr
   int64_t ldq, ldk, ldv, lddo, lddq, lddk, lddv;
   int64_t bsq, bsk, bsv, bsdo, bsdq, bsdk, bsdv;
   int B, H, Nq, Nk, head_dim;

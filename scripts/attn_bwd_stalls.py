@@ -18,7 +18,7 @@ lse = ops.lse_buffer(B, H, N, dev)
 do = torch.randn(B, N, inner, device=dev, generator=g).bfloat16()
 dqkv = torch.empty_like(qkv)
 ops.attention_train(q, k, v, o, H, 0.125, lse)
-dbg = torch.zeros(B * H * (N // 128), 8, device=dev, dtype=torch.int64)
+dbg = torch.zeros(256, 8, device=dev, dtype=torch.int64)
 args = (q, k, v, o, do, lse, dqkv[..., :inner], dqkv[..., inner:2 * inner], dqkv[..., 2 * inner:], H, 0.125)
 for _ in range(3):
     ops.attention_bwd(*args)
@@ -31,9 +31,9 @@ e.record(); torch.cuda.synchronize()
 print(f"attn bwd B={B}: {s.elapsed_time(e) / 10:.3f} ms")
 ops.attention_bwd(*args, debug=dbg)
 torch.cuda.synchronize()
-d = dbg.double().mean(0).tolist()
-T = N // 128
-print("last kernel (dQ), mean cycles per CTA:")
-print(f"  MMA thread : total {d[3]:.0f}  -> {d[3] / T:.0f} / iteration")
-print(f"  compute w0 per iteration: tcgen05.ld+wait {d[1] / T:.0f}  math {d[2] / T:.0f}  tcgen05.st+wait {d[0] / T:.0f}")
-print(f"  compute w0 : wait S (sum) {d[4]:.0f}  wait acc (sum) {d[5]:.0f}  loop {d[6]:.0f} ({d[6] / T:.0f} / iteration)  epilogue {d[7]:.0f}")
+n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+d = dbg[:n_sm].double().mean(0).tolist()
+steps = B * H * (N // 128) * (N // 128) / n_sm
+print(f"last kernel (dQ), mean cycles per CTA ({steps:.0f} steps each):")
+print(f"  MMA thread : wait s_free {d[0] / steps:.0f}  wait C {d[1] / steps:.0f}  wait P {d[2] / steps:.0f}  total {d[3] / steps:.0f} per step")
+print(f"  compute w0 : wait S {d[4] / steps:.0f}  wait acc {d[5] / steps:.0f}  math {d[6] / steps:.0f} per step;  epilogue {d[7] / (steps / (N // 128)):.0f} per item")
