@@ -235,7 +235,9 @@ int pm_ce_label_smooth(const float* logits, int64_t ld, int32_t M, int32_t V, co
  *                         branch of layers.py:55-56), dgamma_dbeta[2, D] = (sum dn * xhat, sum dn).
  *                         work: pm_layernorm_bwd_workspace_floats(M, D) floats.
  *   pm_swiglu_bwd       : hidden = silu(x1) * x2 backward (mlp.py:29-30) on the tile-interleaved x12 the packed w12
- *                         projection produces; also re-materialises `h` (operand of the w3 weight gradient).
+ *                         projection produces; also re-materialises `h` (operand of the w3 weight gradient) and, when
+ *                         b12 != NULL, the bias gradient of w12 (column sums of d12, [2 hp] in the packed order) in the
+ *                         same pass.  work: pm_swiglu_bwd_workspace_floats(M, hp) floats (with b12) or NULL.
  *   pm_attn_bwd         : backward of softmax(scale Q K^T) V (attention.py:52-57): dq, dk, dv from q, k, v, o, d_o and
  *                         the forward's lse.  delta: [2, B, H, lse_ld] fp32 scratch.  Ragged token counts are masked.
  *   pm_vq_bwd           : VectorQuantizer backward (quantize.py:19,29-36): straight-through estimator + both loss
@@ -273,8 +275,9 @@ int pm_colsum_bf16(const void* x, int64_t ld, int32_t M, int32_t N, float* work,
 int64_t pm_layernorm_bwd_workspace_floats(int32_t M, int32_t D);
 int pm_layernorm_bwd(const void* dn, int64_t lddn, const void* x, int64_t ldx, const float* gamma, const void* dres, int64_t ldres,
                      void* dx, int64_t lddx, int32_t M, int32_t D, float eps, float* work, float* dgamma_dbeta, void* stream);
+int64_t pm_swiglu_bwd_workspace_floats(int32_t M, int32_t hp);
 int pm_swiglu_bwd(const void* x12, int64_t ld12, const void* dh, int64_t lddh, void* h, int64_t ldh, void* d12, int64_t ldd12,
-                  int32_t M, int32_t hp, void* stream);
+                  int32_t M, int32_t hp, float* work, float* b12, void* stream);
 int pm_vq_bwd(const float* z, int64_t ldz, const int64_t* idx, const float* E, int32_t e_dim, const float* d_out, int64_t ldd,
               const float* d_loss, float beta, int32_t M, float* dz, void* dz_split, float* dE, void* stream);
 int pm_unpatchify8_bwd(const float* d_img, const float* rec, void* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);

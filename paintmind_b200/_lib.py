@@ -130,7 +130,7 @@ EXPORTS = {
     "pm_wgrad_bf16": [_p, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _i64, _i32, _p],
     "pm_colsum_bf16": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],
     "pm_layernorm_bwd": [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _i32, _i32, _f, _p, _p, _p],
-    "pm_swiglu_bwd": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i32, _i32, _p],
+    "pm_swiglu_bwd": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p],
     "pm_vq_bwd": [_p, _i64, _p, _p, _i32, _p, _i64, _p, _f, _i32, _p, _p, _p, _p],
     "pm_unpatchify8_bwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _p],
 }
@@ -139,6 +139,7 @@ WORKSPACE_QUERIES = {
     "pm_wgrad_workspace_floats": 3,
     "pm_colsum_workspace_floats": 2,
     "pm_layernorm_bwd_workspace_floats": 2,
+    "pm_swiglu_bwd_workspace_floats": 2,
 }
 
 

@@ -134,9 +134,14 @@ int pm_layernorm_bwd(const void* dn, int64_t lddn, const void* x, int64_t ldx, c
   return pm_ln_bwd_launch(dn, lddn, x, ldx, gamma, dres, ldres, dx, lddx, M, D, eps, work, dgamma_dbeta, static_cast<cudaStream_t>(stream));
 }
 
+int64_t pm_swiglu_bwd_workspace_floats(int32_t M, int32_t hp) {
+  if (M <= 0 || hp <= 0) return 0;
+  return static_cast<int64_t>(pm_swiglu_bwd_chunks(M, hp)) * 2 * hp;
+}
+
 int pm_swiglu_bwd(const void* x12, int64_t ld12, const void* dh, int64_t lddh, void* h, int64_t ldh, void* d12, int64_t ldd12,
-                  int32_t M, int32_t hp, void* stream) {
-  return pm_swiglu_bwd_launch(x12, ld12, dh, lddh, h, ldh, d12, ldd12, M, hp, static_cast<cudaStream_t>(stream));
+                  int32_t M, int32_t hp, float* work, float* b12, void* stream) {
+  return pm_swiglu_bwd_launch(x12, ld12, dh, lddh, h, ldh, d12, ldd12, M, hp, work, b12, static_cast<cudaStream_t>(stream));
 }
 
 int pm_vq_bwd(const float* z, int64_t ldz, const int64_t* idx, const float* E, int32_t e_dim, const float* d_out, int64_t ldd,

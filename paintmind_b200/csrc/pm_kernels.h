@@ -146,8 +146,9 @@ int pm_ln_bwd_blocks(int M);
 int pm_ln_bwd_launch(const void* dn, int64_t lddn, const void* x, int64_t ldx, const float* gamma, const void* dres,
                      int64_t ldres, void* dx, int64_t lddx, int M, int D, float eps, float* part, float* dgamma_dbeta,
                      cudaStream_t stream);
+int pm_swiglu_bwd_chunks(int M, int hp);
 int pm_swiglu_bwd_launch(const void* x12, int64_t ld12, const void* dh, int64_t lddh, void* h, int64_t ldh, void* d12,
-                         int64_t ldd12, int M, int hp, cudaStream_t stream);
+                         int64_t ldd12, int M, int hp, float* work, float* b12, cudaStream_t stream);
 int pm_vq_bwd_launch(const float* z, int64_t ldz, const long long* idx, const float* E, const float* d_out, int64_t ldd,
                      const float* d_loss, float beta, int M, float* dz, void* dz_split, float* dE, cudaStream_t stream);
 int pm_unpatchify_bwd_launch(const float* g, const float* rec, void* out, int B, int C, int H, int W, cudaStream_t stream);

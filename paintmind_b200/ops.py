@@ -377,13 +377,16 @@ def layernorm_bwd(dn, x, gamma, dx, dgamma_dbeta, dres=None, eps=1e-5):
     return dx
 
 
-def swiglu_bwd(x12, dh, h, d12):
-    _require_cuda(x12, dh, d12)
+def swiglu_bwd(x12, dh, h, d12, b12=None):
+    """d12 (and h) from x12, dh; b12 (fp32 [2 hp], optional) = column sums of d12 in the packed order, from the same pass."""
+    _require_cuda(x12, dh, d12, b12)
     M, hp = dh.shape
+    lib = _lib.load()
+    work = _workspace("swiglu_bwd", lib.pm_swiglu_bwd_workspace_floats(M, hp), dh.device) if b12 is not None else None
     t0 = _prof_begin()
-    _lib.check(_lib.load().pm_swiglu_bwd(_ptr(x12), x12.stride(0), _ptr(dh), dh.stride(0), _ptr(h), h.stride(0) if h is not None else 0,
-                                         _ptr(d12), d12.stride(0), M, hp, _stream()), "pm_swiglu_bwd")
-    _prof_end(t0, ("swiglu_bwd", M, hp))
+    _lib.check(lib.pm_swiglu_bwd(_ptr(x12), x12.stride(0), _ptr(dh), dh.stride(0), _ptr(h), h.stride(0) if h is not None else 0,
+                                 _ptr(d12), d12.stride(0), M, hp, _ptr(work), _ptr(b12), _stream()), "pm_swiglu_bwd")
+    _prof_end(t0, ("swiglu_bwd", M, hp), 2 if b12 is not None else 1)
 
 
 def vq_bwd(z, idx, E, d_out, d_loss, beta, dz=None, dz_split=None, dE=None):

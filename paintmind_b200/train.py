@@ -220,14 +220,13 @@ class Stage1TrainEngine:
         b3 = torch.empty(D, **f32)
         ops.colsum(dx, b3)
         ops.gemm(dx, bw.w_3_t, dh, bn=256 if M >= 256 else 0)      # 1408 = 5.5 x 256: CTA pairs with a ragged last tile beat bn = 128
-        ops.swiglu_bwd(x12, dh, h, d12)
+        b12 = torch.empty(2 * hp, **f32)
+        ops.swiglu_bwd(x12, dh, h, d12, b12)                 # + bias gradient of w12 (column sums of d12) in the same pass
         w3 = torch.empty(D, hp, **f32)
         ops.wgrad(dx, h, w3)
         ops.layernorm(x_mid, gamma=bw.g2, beta=bw.b2, y=nbuf)
         w12 = torch.empty(2 * hp, D, **f32)
-        b12 = torch.empty(2 * hp, **f32)
         ops.wgrad(d12, nbuf, w12)
-        ops.colsum(d12, b12)
         ops.gemm(d12, bw.w_12_t, dn)
         gb2 = torch.empty(2, D, **f32)
         ops.layernorm_bwd(dn, x_mid, bw.g2, dx_mid, gb2, dres=dx, eps=LN_EPS)

@@ -119,7 +119,8 @@ if want("swiglu"):
     M, hp = 2048, 1408
     x12 = rnd(M, 2 * hp).to(torch.bfloat16); dh = rnd(M, hp).to(torch.bfloat16)
     h = torch.empty(M, hp, device=dev, dtype=torch.bfloat16); d12 = torch.empty(M, 2 * hp, device=dev, dtype=torch.bfloat16)
-    ops.swiglu_bwd(x12, dh, h, d12)
+    b12 = torch.empty(2 * hp, device=dev)
+    ops.swiglu_bwd(x12, dh, h, d12, b12)
     t = x12.float().view(M, hp // 128, 2, 128)
     gg = t[:, :, 0].reshape(M, hp).clone().requires_grad_(True); vv = t[:, :, 1].reshape(M, hp).clone().requires_grad_(True)
     hr = F.silu(gg) * vv
@@ -127,11 +128,13 @@ if want("swiglu"):
     report("swiglu_bwd h", h, hr, 1e-2)
     dref = torch.stack([gg.grad.view(M, hp // 128, 128), vv.grad.view(M, hp // 128, 128)], dim=2).reshape(M, 2 * hp)
     report("swiglu_bwd d12", d12, dref, 1e-2)
+    report("swiglu_bwd b12 (fused column sums)", b12, dref.sum(0), 1e-4)
     if not quick:
         M = 262144
         x12 = rnd(M, 2 * hp).to(torch.bfloat16); dh = rnd(M, hp).to(torch.bfloat16)
         h = torch.empty(M, hp, device=dev, dtype=torch.bfloat16); d12 = torch.empty(M, 2 * hp, device=dev, dtype=torch.bfloat16)
-        ms = timeit(lambda: ops.swiglu_bwd(x12, dh, h, d12))
+        b12 = torch.empty(2 * hp, device=dev)
+        ms = timeit(lambda: ops.swiglu_bwd(x12, dh, h, d12, b12))
         log(f"   swiglu_bwd 262144x1408: {ms:.3f} ms  {6 * M * hp * 2 / ms / 1e6:.0f} GB/s")
         del x12, dh, h, d12
 

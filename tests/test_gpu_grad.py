@@ -80,13 +80,18 @@ def test_swiglu_bwd(ops):
     M, hp = 1024, 384
     x12, dh = rnd(gen, M, 2 * hp).bfloat16(), rnd(gen, M, hp).bfloat16()
     h, d12 = torch.empty(M, hp, device="cuda", dtype=torch.bfloat16), torch.empty(M, 2 * hp, device="cuda", dtype=torch.bfloat16)
-    ops.swiglu_bwd(x12, dh, h, d12)
+    b12 = torch.empty(2 * hp, device="cuda")
+    ops.swiglu_bwd(x12, dh, h, d12, b12)
     t = x12.float().view(M, hp // 128, 2, 128)
     g, v = t[:, :, 0].reshape(M, hp).clone().requires_grad_(True), t[:, :, 1].reshape(M, hp).clone().requires_grad_(True)
     hr = F.silu(g) * v                                          # modules/mlp.py:29-30
     hr.backward(dh.float())
     dref = torch.stack([g.grad.view(M, -1, 128), v.grad.view(M, -1, 128)], dim=2).reshape(M, 2 * hp)
     assert rel_l2(h, hr) < 4e-3 and rel_l2(d12, dref) < 4e-3
+    assert rel_l2(b12, dref.sum(0)) < 1e-5                      # bias gradient of w12 (packed order), summed in fp32 before rounding
+    d12b = torch.empty_like(d12)
+    ops.swiglu_bwd(x12, dh, None, d12b)                         # without h / without the sums
+    assert torch.equal(d12, d12b)
 
 
 @pytest.mark.parametrize("B,H,N", [(2, 8, 1024), (1, 2, 128), (2, 2, 64), (2, 3, 200)])
