@@ -184,3 +184,31 @@ def test_return_dtypes_under_cuda_autocast(cuda_device):
     assert z_q.dtype == torch.float32 and loss.dtype == torch.float32 and idx.dtype == torch.int64
     assert rec.dtype == torch.bfloat16 and rec32.dtype == torch.float32
     assert torch.equal(rec, rec32.to(torch.bfloat16))
+
+
+@pytest.mark.gpu
+def test_graphed_encode_decode_matches_eager_and_follows_weight_updates(cuda_device):
+    """VQModel.graphed(): the CUDA-graph replay of encode + decode is bit-identical to the eager calls, accepts new inputs of
+    the captured shape, and is re-captured when a parameter changes (small-batch serving path)."""
+    import torch
+    import paintmind_b200 as pm
+    from paintmind_b200.config import ver2cfg
+    from paintmind_b200.utils import synthetic
+    cfg = ver2cfg["vit-tiny-test"]
+    model = pm.create_model(arch="vqgan", version="vit-tiny-test", pretrained=False)
+    model.load_state_dict(synthetic.make_vqgan_state_dict(cfg, seed=7), strict=True)
+    model = model.to(cuda_device).eval()
+    x1 = synthetic.make_images(4, 64, seed=1).to(cuda_device)
+    x2 = synthetic.make_images(4, 64, seed=2).to(cuda_device)
+    run = model.graphed(x1)
+    for x in (x1, x2, x1):
+        rec_g, loss_g, idx_g, z_g = [t.clone() for t in run(x)]
+        z, loss, idx = model.encode(x)
+        rec = model.decode(z)
+        assert torch.equal(rec, rec_g) and torch.equal(idx, idx_g) and torch.equal(z, z_g) and torch.equal(loss, loss_g)
+    with torch.no_grad():
+        model.decoder.proj.bias.add_(0.25)                     # bumps the parameter version -> packed operands and the graph are stale
+    rec_g = run(x2)[0].clone()
+    assert torch.equal(rec_g, model.decode(model.encode(x2)[0]))
+    with pytest.raises(RuntimeError):
+        run(x1[:2])
