@@ -539,6 +539,38 @@ class Stage2Engine:
         return self._run(zs, B, N, context)
 
 
+def _graphed_forward_from_ids(self, ids, table, context=None):
+    """forward_from_ids replayed from a CUDA graph (one per (shape, table, context, weights)): a MaskGIT step of the
+    211 M-parameter transformer is ~100 launches; at 8 images per GPU (BASELINE configs[4] sharded over 8 GPUs) their host
+    side is ~15 % of the step.  `ids` are copied into the captured buffer; the returned logits are STATIC (overwritten by the
+    next replay) — Pipeline.sample consumes them before the next step."""
+    self._ensure_packed()
+    ckey = None if context is None else (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
+    key = (tuple(ids.shape), ids.device.index, table.data_ptr(), table._version, ckey, self._fp)
+    g = self.__dict__.get("_graph")
+    if g is None or g["key"] != key:
+        ids_static = ids.detach().to(torch.int64).contiguous().clone()
+        cur = torch.cuda.current_stream(ids.device)
+        side = torch.cuda.Stream(device=ids.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):                       # sizes the workspace, fills the context K/V cache
+                self.forward_from_ids(ids_static, table, context)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(ids.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            logits = self.forward_from_ids(ids_static, table, context)
+        g = dict(key=key, graph=graph, ids=ids_static, logits=logits, context=context, table=table)   # keep the captured operands alive
+        self.__dict__["_graph"] = g
+    g["ids"].copy_(ids, non_blocking=True)
+    g["graph"].replay()
+    return g["logits"]
+
+
+Stage2Engine.forward_from_ids_graphed = _graphed_forward_from_ids
+
+
 def engine_for(module):
     """Engine for a stand-alone Encoder or Decoder module (cached on the module)."""
     eng = module.__dict__.get("_pm_engine")

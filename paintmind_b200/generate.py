@@ -62,6 +62,7 @@ class Pipeline(nn.Module):
         nn.init.normal_(self.mask_token, std=0.02)
         self._rng_seed = None
         self._rng_calls = 0
+        self.cuda_graph = None        # None: replay the transformer forward from a CUDA graph when the batch is small; True / False force it
         self._table = None
         self._table_fp = None
 
@@ -185,7 +186,10 @@ class Pipeline(nn.Module):
         eng = self.transformer.engine()
         ids = ids.to(torch.int64).contiguous().clone()
         context = self._embed_text(text, dev) if text is not None else None
-        logits = eng.forward_from_ids(ids, table, context)                      # fp32 [B, N, V]
+        # small batches are launch-bound on the host: replay the transformer forward from a CUDA graph (cuda_graph = None: auto)
+        use_graph = self.cuda_graph if self.cuda_graph is not None else (B * N <= 16 * 1024)
+        fwd = eng.forward_from_ids_graphed if use_graph else eng.forward_from_ids
+        logits = fwd(ids, table, context)                                       # fp32 [B, N, V]
         pred_ids = torch.empty(B, N, device=dev, dtype=torch.int64)
         scores = torch.empty(B, N, device=dev, dtype=torch.float32)
         if self._rng_seed is None:

@@ -176,6 +176,25 @@ def test_pipeline_generate_runs_schedule(cuda_device, full_pipeline):
     assert all(float(i.min()) >= -1 and float(i.max()) <= 1 for i in imgs)
 
 
+def test_pipeline_generate_cuda_graph_equals_eager(cuda_device, full_pipeline):
+    """Small batches replay the transformer forward from a CUDA graph (Pipeline.cuda_graph): same images, bit for bit, and the
+    graph follows a changed text context."""
+    pipe = full_pipeline
+    g = torch.Generator().manual_seed(5)
+    outs = {}
+    for mode in (False, True):
+        pipe.cuda_graph = mode
+        res = []
+        for text_seed in (1, 2):
+            text = torch.randn(2, 77, 1024, generator=torch.Generator().manual_seed(text_seed)).to(cuda_device)
+            pipe._rng_seed, pipe._rng_calls = 99, 0
+            res.append(pipe.generate(text, timesteps=3, temperature=1.0, topk=5, save_interval=3)[0])
+        outs[mode] = res
+    pipe.cuda_graph = None
+    assert all(torch.equal(a, b) for a, b in zip(outs[False], outs[True]))
+    assert not torch.equal(outs[True][0], outs[True][1])
+
+
 def _run_sample(logits2d, u2d, topk, temp, V):
     from paintmind_b200 import ops
     M = logits2d.shape[0]
