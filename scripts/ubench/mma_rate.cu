@@ -25,6 +25,8 @@ __global__ void k(int mode, int N, int iters, int rot, long long* out) {
     const uint32_t id_ts64 = umma_idesc_bf16(128, 64, 0, 1);
     const uint64_t da = umma_desc_sw128(base), db = umma_desc_sw128(base + 32768);
     const uint64_t dam = umma_desc_sw128_mn(base, 8192), dbm = umma_desc_sw128_mn(base + 32768, 8192);
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const uint32_t d = tm + (rot ? (i & 1) * 256 : 0);
@@ -39,15 +41,17 @@ __global__ void k(int mode, int N, int iters, int rot, long long* out) {
     umma_commit(&bar);
     mbar_wait(&bar, 0);
     out[0] = clock64() - t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    out[1] = static_cast<long long>(g1 - g0);
   }
   tc_fence_before(); __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
 }
 
 int main() {
-  long long* d; cudaMalloc(&d, 8);
+  long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  const int iters = 2000;
+  const int iters = 20000;
   struct { int mode, N, rot; const char* name; } cases[] = {
       {0, 64, 0, "SS K-major  128x64x16 "}, {0, 128, 0, "SS K-major  128x128x16"}, {0, 256, 0, "SS K-major  128x256x16"},
       {1, 64, 0, "TS B=MN     128x64x16 "}, {1, 128, 0, "TS B=MN     128x128x16"}, {2, 128, 0, "SS MN/MN    128x128x16"},
@@ -55,8 +59,9 @@ int main() {
       {0, 64, 1, "SS 128x64x16 2 accums "}, {1, 64, 1, "TS 128x64x16 2 accums "}};
   for (auto& c : cases) {
     k<<<1, 128, 100 * 1024>>>(c.mode, c.N, iters, c.rot, d); cudaDeviceSynchronize();
-    long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    printf("%s: %.1f cycles per MMA%s\n", c.name, double(h) / (iters * 4) / (c.mode == 3 ? 1 : 1), c.mode == 3 ? " pair" : "");
+    long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("%s: %.1f cycles = %.1f ns per MMA%s (SM clock %.0f MHz)\n", c.name, double(h[0]) / (iters * 4), double(h[1]) / (iters * 4),
+           c.mode == 3 ? " pair" : "", 1e3 * double(h[0]) / double(h[1]));
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;

@@ -27,6 +27,8 @@ __global__ void __cluster_dims__(2, 1, 1) k(int mode, int N, int iters, long lon
     const uint32_t tm = slot;
     const uint32_t id_ss = umma_idesc_bf16(256, N, 0, 0), id_ts = umma_idesc_bf16(256, N, 0, 1);
     const uint64_t da = umma_desc_sw128(base), db = umma_desc_sw128(base + 32768);
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
@@ -38,21 +40,24 @@ __global__ void __cluster_dims__(2, 1, 1) k(int mode, int N, int iters, long lon
     umma_commit_2sm(&bar, 1);
     mbar_wait(&bar, 0);
     out[0] = clock64() - t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    out[1] = static_cast<long long>(g1 - g0);
   }
   tc_fence_before(); __syncthreads(); cluster_sync_all();
   if (warp == 0) { tc_fence_after(); tmem_dealloc_2sm(slot, 512); }
 }
 
 int main() {
-  long long* d; cudaMalloc(&d, 8);
+  long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  const int iters = 2000;
+  const int iters = 20000;
   struct { int mode, N; const char* name; } cases[] = {{0, 64, "SS 2sm 256x64x16 "}, {0, 128, "SS 2sm 256x128x16"}, {0, 256, "SS 2sm 256x256x16"},
                                                       {1, 64, "TS 2sm 256x64x16 "}, {1, 128, "TS 2sm 256x128x16"}};
   for (auto& c : cases) {
     k<<<2, 128, 100 * 1024>>>(c.mode, c.N, iters, d); cudaDeviceSynchronize();
-    long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    printf("%s: %.1f cycles per MMA   (%s)\n", c.name, double(h) / (iters * 4), cudaGetErrorString(cudaGetLastError()));
+    long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("%s: %.1f cycles = %.1f ns per MMA (SM clock %.0f MHz)  (%s)\n", c.name, double(h[0]) / (iters * 4), double(h[1]) / (iters * 4),
+           1e3 * double(h[0]) / double(h[1]), cudaGetErrorString(cudaGetLastError()));
   }
   return 0;
 }
