@@ -388,10 +388,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           float4* dst = reinterpret_cast<float4*>(p.o32 + (static_cast<size_t>(it.b) * p.Nq + qrow) * p.ldo32 + it.h * AT_D);
 #pragma unroll
           for (int jv = 0; jv < 8; ++jv) {
-            dst[jv] = make_float4(__uint_as_float(r0[jv * 4 + 0]) * inv_l, __uint_as_float(r0[jv * 4 + 1]) * inv_l,
-                                  __uint_as_float(r0[jv * 4 + 2]) * inv_l, __uint_as_float(r0[jv * 4 + 3]) * inv_l);
-            dst[8 + jv] = make_float4(__uint_as_float(r1[jv * 4 + 0]) * inv_l, __uint_as_float(r1[jv * 4 + 1]) * inv_l,
-                                      __uint_as_float(r1[jv * 4 + 2]) * inv_l, __uint_as_float(r1[jv * 4 + 3]) * inv_l);
+            __stcs(dst + jv, make_float4(__uint_as_float(r0[jv * 4 + 0]) * inv_l, __uint_as_float(r0[jv * 4 + 1]) * inv_l,
+                                         __uint_as_float(r0[jv * 4 + 2]) * inv_l, __uint_as_float(r0[jv * 4 + 3]) * inv_l));
+            __stcs(dst + 8 + jv, make_float4(__uint_as_float(r1[jv * 4 + 0]) * inv_l, __uint_as_float(r1[jv * 4 + 1]) * inv_l,
+                                             __uint_as_float(r1[jv * 4 + 2]) * inv_l, __uint_as_float(r1[jv * 4 + 3]) * inv_l));
           }
         }
       }
