@@ -79,7 +79,9 @@ __device__ __forceinline__ void sched_fence(uint32_t tok) {
 //         idle).  1 = a one-time half-step delay of tile 1 instead.  0 = neither.
 // DEFER : where the wait for the previous P_t V sits: -1 = before the exponentials, c = 0..3 = after the
 //         exponentials of 32-key chunk c (P chunks are stored from there on; 3 = whole row kept in registers)
-template <int EMU, int SPLIT, int DEFER, int CHAIN, int PING>
+// TRAIN : also emit the row log-sum-exp and an fp32 copy of the output (training forward; a separate instantiation so that
+//         the inference kernel's register allocation is untouched: the two epilogue branches cost it 1.5 %)
+template <int EMU, int SPLIT, int DEFER, int CHAIN, int PING, bool TRAIN = false>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -370,7 +372,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tc_fence_after();
       const float l_sum = (la.x + la.y) + (lb.x + lb.y);
       const float inv_l = 1.0f / l_sum;
-      if (p.lse != nullptr) {
+      if (TRAIN && p.lse != nullptr) {
         // training forward: base-2 log-sum-exp of the scaled score row, consumed by pm_attn_bwd
         const int qrow = it.qb * 2 * AT_BM + t * AT_BM + row_in_tile;
         if (qrow < p.Nq) p.lse[(static_cast<size_t>(it.b) * p.H + it.h) * p.lse_ld + qrow] = m_used + log2f(l_sum);
@@ -380,7 +382,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_ld_x32(tO + 32, r1);
       tmem_ld_wait();
       // (O_t is free again: the next item's first P V is only issued after this thread's next p_full arrival)
-      if (p.o32 != nullptr) {
+      if (TRAIN && p.o32 != nullptr) {
         // training forward: an fp32 copy of the output rows, so that delta = rowsum(dO * O) of the backward pass is not
         // limited by O's bf16 rounding (dS = P (dP - delta) cancels to ~1e-3 of its terms when attention is diffuse)
         const int qrow = it.qb * 2 * AT_BM + t * AT_BM + row_in_tile;
@@ -482,11 +484,18 @@ int pm_attn_launch(const AttnParams& p, cudaStream_t stream) {
     }
     fn = v->fn;
   }
-  static bool attr_done[PM_MAX_DEVICES] = {};
-  if ((rc = pm_ensure_dyn_smem(fn, AT_SMEM_BYTES, attr_done)) != 0) return rc;
+  static bool attr_done[PM_MAX_DEVICES] = {}, attr_done_train[PM_MAX_DEVICES] = {};
+  const bool train = p.lse != nullptr || p.o32 != nullptr;
+  AttnKernelFn kern = fn;
+  if (train) {
+    kern = attn_kernel<1, 1, 3, 8, 0, true>;
+    if ((rc = pm_ensure_dyn_smem(kern, AT_SMEM_BYTES, attr_done_train)) != 0) return rc;
+  } else if ((rc = pm_ensure_dyn_smem(fn, AT_SMEM_BYTES, attr_done)) != 0) {
+    return rc;
+  }
   const long long items = static_cast<long long>((p.Nq + 2 * AT_BM - 1) / (2 * AT_BM)) * p.H * p.B;
   const int grid = items < pm_num_sms() ? static_cast<int>(items) : pm_num_sms();
-  fn<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  kern<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return static_cast<int>(cudaGetLastError());
 }
 
