@@ -276,7 +276,9 @@ _WORK = {}
 
 
 def _workspace(name, nfloats, device):
-    """fp32 scratch reused across calls (split-K partial tiles, column-sum partials)."""
+    """fp32 scratch reused across calls (split-K partial tiles, column-sum partials).  One buffer per (purpose, device): calls
+    are ordered by the stream they are enqueued on, so this is safe for the single-stream use of train.py; a host that
+    drives several streams concurrently passes its own workspaces to the C-ABI (every entry point takes them as arguments)."""
     key = (name, str(device))
     t = _WORK.get(key)
     if t is None or t.numel() < nfloats:
