@@ -104,3 +104,24 @@ def test_pipeline_surface_and_schedule():
     ks = [max(int(mask_schedule((s + 1) / 12) * 1024), 1) for s in range(12)]
     assert ks == [1015, 989, 946, 886, 812, 724, 623, 512, 391, 265, 133, 1]      # SURVEY.md §3.3 probe
     assert isinstance(mask_schedule(0.5), np.floating)
+
+
+def test_training_forward_has_no_cpu_fallback():
+    """VQModel.forward under autograd (the generator training step) on a CPU model must fail loudly, like the inference path."""
+    import pytest
+    import torch
+    import paintmind_b200 as pm
+    model = pm.create_model(arch="vqgan", version="vit-tiny-test", pretrained=False).train()
+    x = torch.zeros(1, 3, 64, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(x)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        model(x)
+
+
+def test_allreduce_gradients_is_a_noop_without_a_process_group():
+    import torch
+    from paintmind_b200 import dist as pmdist
+    lin = torch.nn.Linear(3, 2)
+    lin.weight.grad = torch.ones_like(lin.weight)
+    assert pmdist.allreduce_gradients(lin) is None and torch.equal(lin.weight.grad, torch.ones(2, 3))
