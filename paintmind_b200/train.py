@@ -377,5 +377,8 @@ class _VQGANStep(torch.autograd.Function):
 
 
 def vqgan_forward_with_grad(model, img):
+    if img.requires_grad:
+        raise NotImplementedError("paintmind_b200: VQModel.forward produces parameter gradients only; a gradient w.r.t. the input "
+                                  "image is not computed (no caller of the reference needs one) — detach the image")
     names, params = zip(*[(n, p) for n, p in model.named_parameters()])
     return _VQGANStep.apply(model, img, names, *params)

@@ -214,6 +214,15 @@ def test_model_gradients_vs_reference_fixture(cuda_device, cfg_name, fixture):
     assert not bad, bad
 
 
+def test_image_gradient_is_refused_loudly(cuda_device):
+    import paintmind_b200 as pm
+    from paintmind_b200.utils import synthetic
+    model = pm.create_model(arch="vqgan", version="vit-tiny-test", pretrained=False).cuda()
+    img = synthetic.make_images(1, 64, seed=1).cuda().requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        model(img)
+
+
 def test_frozen_model_takes_inference_path(cuda_device):
     import paintmind_b200 as pm
     from paintmind_b200.utils import synthetic
