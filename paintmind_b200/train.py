@@ -11,9 +11,9 @@ Memory plan (M = B * 1024 tokens): the forward keeps ONE bf16 [M, D] checkpoint 
 plus the few tensors at the path's joints (patch rows, pre-norm tokens, latents, indices, final decoder tokens, rec);
 the backward re-runs a block's forward from its checkpoint (qkv, attention + log-sum-exp, x_mid, x12) right before
 differentiating it.  16 checkpoints x 268 MB at B = 256 — 4.3 GB of the 180 GB.  When memory allows (`keep_attention`,
-decided per call from the free HBM) the forward also keeps each block's qkv, attention output (bf16 + fp32) and
-log-sum-exp — 1.6 GB per block at B = 256 — and the backward skips the attention recomputation (the most expensive
-part of it: 1.26 of 2.0 ms per block).
+decided per call from the free HBM) the forward writes every block's qkv, attention output (bf16 + fp32), log-sum-exp,
+x_mid and output to fresh tensors — 2.2 GB per block at B = 256; the block input is then its own checkpoint (no copy)
+and the backward recomputes only x12 (the attention recomputation was the most expensive part: 1.26 of 2.0 ms per block).
 
 Backward of one block (dgrad = pm_gemm_bf16 against the transposed weight, wgrad = pm_wgrad_bf16):
     dh   = dx W3                     dW3 = dx^T h        db3 = colsum(dx)
@@ -127,10 +127,12 @@ class Stage1TrainEngine:
         sv["patches"], sv["x0"] = patches, x0
         keep = self._keep_policy(M, enc.dim, len(e.enc_blocks) + len(e.dec_blocks), dev)
         sv["enc_ckpt"], sv["enc_attn"] = [], []
+        x = x.clone() if keep else x                 # keep=True: blocks write fresh tensors, their inputs ARE the checkpoints
         for blk in e.enc_blocks:
-            sv["enc_ckpt"].append(x.clone())
-            sv["enc_attn"].append(self._block_forward(blk, x, st, B, N, keep))
-        sv["x_enc"] = x.clone()
+            sv["enc_ckpt"].append(x if keep else x.clone())
+            x, kept = self._block_forward(blk, x, st, B, N, keep)
+            sv["enc_attn"].append(kept)
+        sv["x_enc"] = x if keep else x.clone()
         z = torch.empty(M, m.quantize.e_dim, device=dev, dtype=torch.float32)
         ops.gemm(x, e.w_prev, z, bias=e.b_prev, out_mode=PM_OUT_F32, bn=32)
         r = m.quantize.quantize_2d(z, want_split=True)
@@ -142,10 +144,12 @@ class Stage1TrainEngine:
         st = _RowStats(ws, M, Dd, dev)
         ops.gemm(r["zq_split"], e.w_post, xd, bias=e.b_post, stats_out=st.produce(), **e.dec_pos)
         sv["dec_ckpt"], sv["dec_attn"] = [], []
+        xd = xd.clone() if keep else xd
         for blk in e.dec_blocks:
-            sv["dec_ckpt"].append(xd.clone())
-            sv["dec_attn"].append(self._block_forward(blk, xd, st, B, N, keep))
-        sv["x_dec"] = xd.clone()
+            sv["dec_ckpt"].append(xd if keep else xd.clone())
+            xd, kept = self._block_forward(blk, xd, st, B, N, keep)
+            sv["dec_attn"].append(kept)
+        sv["x_dec"] = xd if keep else xd.clone()
         rec = torch.empty(B, dec.out_channels, dec.image_size, dec.image_size, device=dev, dtype=torch.float32)
         ops.gemm(xd, e.w_proj_chw, rec, bias=e.b_proj_chw, colsum=e.cs_proj_chw, out_mode=PM_OUT_UNPATCH, patch=8, channels=3,
                  grid=dec.image_size // 8, **st.consume())
@@ -155,16 +159,17 @@ class Stage1TrainEngine:
     def _keep_policy(self, M, D, n_blocks, dev):
         if self.keep_attention is not None:
             return bool(self.keep_attention)
-        per_block = M * D * (3 * 2 + 2 + 4) + M * 8 * 4            # qkv + ao (bf16) + ao (fp32) + lse, inner == D
+        per_block = M * D * (3 * 2 + 2 + 4 + 2 + 2) + M * 8 * 4    # qkv + ao (bf16) + ao (fp32) + x_mid + block output, lse; inner == D
         free, _ = torch.cuda.mem_get_info(dev)
         return n_blocks * per_block < 0.4 * free
 
     def _block_forward(self, blk, x, st, B, N, keep):
-        """One pre-LN block in place on x (same kernels as engine.run_blocks).  keep=True: qkv / attention output /
-        log-sum-exp go to fresh tensors that are returned for the backward pass instead of the shared workspace."""
+        """One pre-LN block (same kernels as engine.run_blocks) -> (block output, kept tensors).  keep=False: in place on x,
+        nothing kept.  keep=True: qkv / attention output / log-sum-exp / x_mid / the block output go to fresh tensors: x itself
+        is left intact (it is the block's checkpoint — no copy), and the backward pass recomputes only x12."""
         if not keep:
             run_blocks([blk], x, st, B, N, self.eng.ws)
-            return None
+            return x, None
         M, D = x.shape
         dev = x.device
         inner, H = blk.inner, blk.heads
@@ -175,11 +180,13 @@ class Stage1TrainEngine:
         ops.gemm(x, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, **st.consume())
         q3 = qkv.view(B, N, 3 * inner)
         ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32)
-        ops.gemm(ao, blk.w_o, x, bias=blk.b_o, res=x, stats_out=st.produce())
+        x_mid = torch.empty_like(x)
+        ops.gemm(ao, blk.w_o, x_mid, bias=blk.b_o, res=x, stats_out=st.produce())
         h = self.eng.ws.get("h", (M, blk.hp), torch.bfloat16, dev)
-        ops.gemm(x, blk.w_12, h, bias=blk.b_12, colsum=blk.cs_12, swiglu=True, **st.consume())
-        ops.gemm(h, blk.w_3, x, bias=blk.b_3, res=x, stats_out=st.produce())
-        return (qkv, ao, ao32, lse)
+        ops.gemm(x_mid, blk.w_12, h, bias=blk.b_12, colsum=blk.cs_12, swiglu=True, **st.consume())
+        x_out = torch.empty_like(x)
+        ops.gemm(h, blk.w_3, x_out, bias=blk.b_3, res=x_mid, stats_out=st.produce())
+        return x_out, (qkv, ao, ao32, lse, x_mid)
 
     # ---------------------------------------------------------------------------------------- backward
     def _block_backward(self, blk, bw, x_in, dx, B, N, grads, prefix, kept=None):
@@ -192,12 +199,12 @@ class Stage1TrainEngine:
         bf = torch.bfloat16
         # ---- recompute the block's forward from its checkpoint ----
         stats = ws.get("stats", (M, 2), torch.float32, dev)
-        x_mid = ws.get("x_mid", (M, D), bf, dev)
         x12 = ws.get("x12", (M, 2 * hp), bf, dev)
         if kept is not None:
-            qkv, ao, ao32, lse = kept
+            qkv, ao, ao32, lse, x_mid = kept
             q3 = qkv.view(B, N, 3 * inner)
         else:
+            x_mid = ws.get("x_mid", (M, D), bf, dev)
             qkv = ws.get("qkv", (M, 3 * inner), bf, dev)
             ao = ws.get("ao", (M, inner), bf, dev)
             lse = ws.get("lse", (B, H, (N + 127) // 128 * 128), torch.float32, dev)[:, :, :N]
@@ -206,7 +213,7 @@ class Stage1TrainEngine:
             ops.gemm(x_in, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, stats=stats)
             q3 = qkv.view(B, N, 3 * inner)
             ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32)
-        ops.gemm(ao, blk.w_o, x_mid, bias=blk.b_o, res=x_in)
+            ops.gemm(ao, blk.w_o, x_mid, bias=blk.b_o, res=x_in)
         ops.layernorm(x_mid, stats=stats)
         ops.gemm(x_mid, blk.w_12, x12, bias=blk.b_12, colsum=blk.cs_12, stats=stats)          # plain store: gate | value tiles
         # ---- feed-forward branch ----
