@@ -4,15 +4,16 @@
 // out = einsum(attn, v)) — SURVEY.md §8f row 4.  With P = softmax(scale * Q K^T) recomputed from the forward's
 // row log-sum-exp (base 2, `lse`) and delta = rowsum(dO ⊙ O):
 //     dV = P^T dO          dS = P ⊙ (dO V^T - delta) * scale          dQ = dS K          dK = dS^T Q
-// Two launches of one persistent kernel template, no atomics, deterministic:
-// Token counts need not be multiples of 128: TMA zero-fills / clips the ragged tiles and the tail columns are masked.
-//   DKV = false : CTA = (128-query tile, head, batch), loops over key tiles.   rows = queries, columns = keys
+// Two launches of one persistent kernel template, no atomics, deterministic.  Token counts need not be multiples of 128:
+// TMA zero-fills / clips the ragged tiles and the tail columns are masked.
+//   DKV = false : work item = (128-query tile, head, image), loops over key tiles.   rows = queries, columns = keys
 //                 S' = Q K_j^T,  dP' = dO V_j^T,  dQ += dS' K_j
-//   DKV = true  : CTA = (128-key tile, head, batch), loops over query tiles.  rows = keys, columns = queries
+//   DKV = true  : work item = (128-key tile, head, image), loops over query tiles.  rows = keys, columns = queries
 //                 S' = K Q_i^T (= S^T),  dP' = V dO_i^T,  dV += P' dO_i,  dK += dS' Q_i
-// In both, the two score-shaped products are SS MMAs (both operands K-major, 128 x 128 x 64) into TMEM; 128 threads
-// (one per TMEM lane = row) turn them into P' and dS' (packed bf16, written back to TMEM), which then feed TS MMAs
-// (A from TMEM, B = the very same shared-memory tile re-read as an MN-major operand — no transposes anywhere).
+// In both, the two score-shaped products are SS MMAs (both operands K-major, 128 x 128 x 64) into TMEM; 256 threads
+// (two warpgroups: one thread per TMEM lane = row and 64-column half) turn them into P' and dS' (packed bf16, written back
+// to TMEM), which then feed TS MMAs (A from TMEM, B = the very same shared-memory tile re-read as an MN-major operand —
+// no transposes anywhere).
 #include "pm_common.cuh"
 #include "pm_kernels.h"
 
@@ -52,7 +53,7 @@ __device__ __forceinline__ float ab_ex2(float x) {
 //  no throughput gain on sm_100a, 3.27 ms against 2.96 ms.)
 
 // Work split inside a CTA: the two score-shaped products of a step are issued for the whole 128-column tile (measured on
-// B200, scripts/ubench/mma_rate.cu: one tcgen05.mma with M = 128 costs ~73 cycles (SS) / ~82 cycles (TS) whatever N <= 128
+// B200, scripts/ubench/mma_rate.cu: one tcgen05.mma with M = 128 costs ~73 cycles (SS) / ~84 cycles (TS) whatever N <= 128
 // is, so instruction COUNT is what the tensor pipe is bound by and N = 128 is the efficient shape), then compute
 // warpgroup g (warps 4g .. 4g+3, one thread per row) turns columns [64g, 64g + 64) into P' / dS': two compute warps share
 // every SM sub-partition (one warp per scheduler cannot hide its own MUFU / TMEM latencies).  The accumulating TS MMAs of
