@@ -325,10 +325,11 @@ class Stage1TrainEngine:
         # ---- quantizer: straight-through + both loss terms (quantize.py:19,29-36) ----
         E = m.quantize.embedding.weight.detach().float().contiguous()
         dzs = ws.get("dz_split", (M, 64), bf, dev)
-        dE = torch.zeros_like(E)
         dl = d_loss.detach().float().reshape(1).contiguous() if d_loss is not None else None
+        dE = torch.zeros_like(E) if dl is not None else None       # the codebook only hears from the loss terms (quantize.py:33,36)
         ops.vq_bwd(sv["z"], sv["idx"], E, d_zq, dl, m.quantize.beta, dz=None, dz_split=dzs, dE=dE)
-        grads["quantize.embedding.weight"] = dE
+        if dE is not None:
+            grads["quantize.embedding.weight"] = dE
         # ---- prev_quant (vqmodel.py:23) ----
         De = enc.dim
         wprev = torch.empty(64, De, **f32)
