@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+NVCC_FLAGS += os.environ.get("PM_NVCC_EXTRA", "").split()      # bring-up builds, e.g. -DPM_VQ_DEBUG (part of the digest)
 if os.environ.get("PM_DEBUG"):
     NVCC_FLAGS.append("-DPM_MBAR_PRINTF")     # print which mbarrier timed out before trapping
 

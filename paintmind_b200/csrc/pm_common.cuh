@@ -213,6 +213,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// K-major operand with 64-byte rows (K = 32 bf16) and the 64B swizzle: 8-row / 512-byte atoms, SBO = 512 B.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);         // start address  [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                              // LBO (unused)   [16,30)
+  d |= static_cast<uint64_t>(512 >> 4) << 32;                       // SBO            [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                              // version = 1    [46,48)
+  d |= static_cast<uint64_t>(4) << 61;                              // SWIZZLE_64B    [61,64)
+  return d;
+}
+
 // MN-major operand wider than one 64-element swizzle atom along M/N: `lbo_bytes` = distance between consecutive
 // 64-element groups (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units); SBO = 1024 B per 8 k-rows.
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -298,6 +309,19 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
+// Pins the first use of an asynchronously loaded register array behind the tcgen05.wait::ld that precedes this call (an
+// empty volatile asm that "modifies" the registers: arithmetic on them cannot be hoisted above it).
+__device__ __forceinline__ void reg_fence64(uint32_t (&r)[64]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]), "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39]), "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]), "+r"(r[46]), "+r"(r[47]), "+r"(r[48]), "+r"(r[49]), "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]), "+r"(r[55]), "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]), "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])::"memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -395,6 +419,8 @@ int pm_get_encode_fn(PFN_encodeTiled* out);
 // box = [box_rows, box_cols]; 128B swizzle requires box_cols * elt_bytes == 128.
 int pm_make_tmap_2d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t rows,
                     uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+int pm_make_tmap_2d_sw64(CUtensorMap* map, const void* base, int elt_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                         uint32_t box_rows, uint32_t box_cols);
 // 3-D tensor [batch, rows, cols] (cols contiguous), strides in elements.
 int pm_make_tmap_3d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t batch,
                     uint64_t rows, uint64_t cols, uint64_t ld_row, uint64_t ld_batch,

@@ -38,6 +38,24 @@ int pm_make_tmap_2d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t 
   return r == CUDA_SUCCESS ? PM_OK : PM_ERR_TENSORMAP;
 }
 
+// 64-byte rows (box_cols * elt_bytes == 64) with the 64B swizzle: K = 32 bf16 operand tiles (pm_vq.cu)
+int pm_make_tmap_2d_sw64(CUtensorMap* map, const void* base, int elt_bytes, uint64_t rows, uint64_t cols,
+                         uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc;
+  int rc = pm_get_encode_fn(&enc);
+  if (rc != PM_OK) return rc;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * elt_bytes) & 15) != 0) return PM_ERR_INVALID;
+  if (box_cols * elt_bytes != 64 || box_rows > 256) return PM_ERR_INVALID;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * elt_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype_of(elt_bytes), 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PM_OK : PM_ERR_TENSORMAP;
+}
+
 int pm_make_tmap_3d(CUtensorMap* map, const void* base, int elt_bytes, uint64_t batch, uint64_t rows,
                     uint64_t cols, uint64_t ld_row, uint64_t ld_batch, uint32_t box_rows,
                     uint32_t box_cols) {

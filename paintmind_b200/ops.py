@@ -150,6 +150,17 @@ def vq_codebook_prep(E, en=None, packed=None):
     return en, packed
 
 
+def vq_splits(M, n_e):
+    """Codebook splits pm_vq_fwd picks for splits = 0 (mirrors pm_vq_launch): > 1 only when the 256-row tiles alone cannot
+    fill the SMs; the split path needs the cand_val / cand_idx scratch."""
+    row_tiles = (M + 255) // 256
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    s = 1
+    while row_tiles * s < sms and (n_e // (s * 2)) >= 8 * 128 and (n_e % (s * 2 * 128)) == 0 and s < 8:
+        s *= 2
+    return s
+
+
 def vq_forward(z2d, en, packed, *, idx, zq=None, zq_split=None, sse=None, hist=None, cand_val=None, cand_idx=None,
                splits=0):
     _require_cuda(z2d, en, packed, idx)
@@ -162,7 +173,7 @@ def vq_forward(z2d, en, packed, *, idx, zq=None, zq_split=None, sse=None, hist=N
     args.M, args.n_e, args.e_dim, args.splits = z2d.shape[0], en.shape[0], en.shape[1], splits
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_vq_fwd(C.byref(args), _stream()), "pm_vq_fwd")
-    _prof_end(t0, ("vq_forward", args.M, args.n_e), 2 if (splits != 1 and args.M < 150000) else 1)
+    _prof_end(t0, ("vq_forward", args.M, args.n_e), 2 if (splits != 1 and cand_val is not None and vq_splits(args.M, args.n_e) > 1) else 1)
 
 
 def vq_gather(idx, table, normalize, out=None, out_split=None):

@@ -19,6 +19,36 @@ class VectorQuantizer(nn.Module):
         self.embedding.weight.data.normal_()
         self._last_hist = None      # codebook usage of the last forward (int64 [n_e]); new in this build
         self._last_sse = None       # sum (z_q - z)^2 of the last forward (float64 [1])
+        self._prep = None           # (key, en, packed): normalised codebook operands, rebuilt when the weight changes
+        self._cand = None           # (key, cand_val, cand_idx): scratch of the split-codebook path (small M only)
+
+    def invalidate(self):
+        """Drop the cached normalised codebook.  Needed only after an in-place write that bypasses autograd's version
+        counter (``embedding.weight.data.copy_(...)``): ``data_ptr`` and ``_version`` are the cache key."""
+        self._prep = None
+
+    def _codebook_operands(self):
+        """(en fp32 [n_e, 32], packed bf16 [n_e, 64]) of the current codebook.  The reference re-normalises the codebook on
+        every forward (quantize.py:21); the result only depends on the weight, so it is cached on (data_ptr, _version,
+        device) of the parameter and rebuilt by the prep kernel when an optimizer step / load_state_dict bumps the version."""
+        w = self.embedding.weight
+        key = (w.data_ptr(), w._version, w.device, w.dtype)
+        if self._prep is None or self._prep[0] != key:
+            E = w.detach()
+            if E.dtype != torch.float32:
+                E = E.float()
+            en, packed = ops.vq_codebook_prep(E.contiguous())
+            self._prep = (key, en, packed)
+        return self._prep[1], self._prep[2]
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._prep = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._prep = None
+        self._cand = None
+        return super()._apply(fn, *args, **kwargs)
 
     def _check(self, t):
         if not t.is_cuda or not self.embedding.weight.is_cuda:
@@ -33,17 +63,19 @@ class VectorQuantizer(nn.Module):
         self._check(z2d)
         M = z2d.shape[0]
         dev = z2d.device
-        E = self.embedding.weight.detach()
-        if E.dtype != torch.float32:
-            E = E.float()
-        en, packed = ops.vq_codebook_prep(E.contiguous())
+        en, packed = self._codebook_operands()
         idx = torch.empty(M, device=dev, dtype=torch.int64)
         zq = torch.empty(M, self.e_dim, device=dev, dtype=torch.float32)
         zs = torch.empty(M, 2 * self.e_dim, device=dev, dtype=torch.bfloat16) if want_split else None
-        sse = torch.zeros(1, device=dev, dtype=torch.float64)
-        hist = torch.zeros(self.n_e, device=dev, dtype=torch.int64)
-        cv = torch.empty(8, M, device=dev, dtype=torch.float32)
-        ci = torch.empty(8, M, device=dev, dtype=torch.int32)
+        # usage histogram (int64 [n_e]) and the squared-error sum (float64 [1]) share one zero-filled allocation: one memset
+        acc = torch.zeros(self.n_e + 1, device=dev, dtype=torch.int64)
+        hist, sse = acc[:self.n_e], acc[self.n_e:].view(torch.float64)
+        cv = ci = None
+        if ops.vq_splits(M, self.n_e) > 1:       # the codebook is only split over several CTAs when M alone cannot fill the GPU
+            if self._cand is None or self._cand[0] != (M, dev):
+                self._cand = ((M, dev), torch.empty(8, M, device=dev, dtype=torch.float32),
+                              torch.empty(8, M, device=dev, dtype=torch.int32))
+            cv, ci = self._cand[1], self._cand[2]
         ops.vq_forward(z2d, en, packed, idx=idx, zq=zq, zq_split=zs, sse=sse, hist=hist, cand_val=cv, cand_idx=ci)
         self._last_hist, self._last_sse = hist, sse
         return dict(idx=idx, zq=zq, zq_split=zs, sse=sse, hist=hist)
@@ -72,8 +104,8 @@ class VectorQuantizer(nn.Module):
         self._check(indices)
         if indices.numel() == 0:
             return torch.empty(*indices.shape, self.e_dim, device=indices.device)
-        E = self.embedding.weight.detach().float().contiguous()
+        en, _ = self._codebook_operands()          # rows of the cached l2norm(E): gathering them IS l2norm(E[idx])
         idx = indices.reshape(-1).to(torch.int64).contiguous()
         out = torch.empty(idx.numel(), self.e_dim, device=idx.device, dtype=torch.float32)
-        ops.vq_gather(idx, E, True, out, None)
+        ops.vq_gather(idx, en, False, out, None)
         return out.reshape(*indices.shape, self.e_dim)

@@ -133,6 +133,77 @@ def test_vq_edge_cases(cuda_device):
             assert idx[0].item() == 3
 
 
+def test_vq_candidate_ring_overflow_falls_back_to_exact_scan(cuda_device):
+    """The 1x-MMA kernel keeps at most 16 near-maximum candidates per row; rows with more codes than that within the
+    bf16 error margin of their best score (duplicated / collapsed codebooks, zero latents) must still return the exact
+    first arg-min: they are re-done by the in-kernel brute-force scan."""
+    from paintmind_b200 import ops
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(11)
+    cases = []
+    # (a) 80 exact duplicates of code 5 and 40 near-duplicates (within 1e-3) ahead of them in index order
+    E = torch.randn(512, 32, generator=gen)
+    E[100:180] = E[5]
+    E[200:240] = E[5] + 1e-3 * torch.randn(40, 32, generator=gen)
+    z = torch.randn(300, 32, generator=gen)
+    z[:10] = E[5] * torch.rand(10, 1, generator=gen).add(0.5) + 1e-4 * torch.randn(10, 32, generator=gen)
+    z[10] = 0.0                                   # zero latent: every distance equal up to fp32 rounding
+    cases.append((z, E))
+    # (b) a fully collapsed codebook: every row overflows the ring
+    E2 = torch.randn(1, 32, generator=gen).repeat(256, 1)
+    cases.append((torch.randn(70, 32, generator=gen), E2))
+    for z, E in cases:
+        for splits in (1, 2):
+            if E.shape[0] % (splits * 128) != 0:
+                continue
+            zd, Ed = z.to(dev), E.to(dev)
+            en, packed = ops.vq_codebook_prep(Ed)
+            M = z.shape[0]
+            idx = torch.empty(M, device=dev, dtype=torch.int64)
+            zq = torch.empty(M, 32, device=dev)
+            cv = torch.empty(8, M, device=dev)
+            ci = torch.empty(8, M, device=dev, dtype=torch.int32)
+            ops.vq_forward(zd, en, packed, idx=idx, zq=zq, cand_val=cv, cand_idx=ci, splits=splits)
+            zn, enr = F.normalize(zd.double(), dim=-1), F.normalize(Ed, dim=-1).double()
+            s = zn @ enr.t()                                         # fp64 scores of the fp32-normalised codebook
+            ref = s.argmax(1)                                        # first index of the maximum
+            top2 = s.topk(2, dim=1).values
+            mism = idx != ref
+            # a different index is only acceptable where it scores the same to fp32 accuracy
+            got = s.gather(1, idx.view(-1, 1)).view(-1)
+            assert torch.all((top2[:, 0] - got)[mism] < 5e-6), (E.shape, splits, int(mism.sum()))
+            if E.shape[0] == 512:
+                assert torch.all(idx[:10] == 5), idx[:10]
+            else:
+                assert torch.all(idx == 0)
+            np.testing.assert_allclose(zq.cpu().numpy(), F.normalize(Ed, dim=-1)[idx].cpu().numpy(), atol=2e-6, rtol=0)
+
+
+def test_vq_codebook_cache_follows_weight_updates(cuda_device):
+    """The normalised codebook is cached on the parameter's (data_ptr, _version): an optimizer-style in-place update or a
+    load_state_dict must be picked up, `.data` writes need invalidate() (documented)."""
+    from paintmind_b200.stage1.quantize import VectorQuantizer
+    gen = torch.Generator().manual_seed(5)
+    vq = VectorQuantizer(256, 32).to(cuda_device)
+    z = torch.randn(2, 64, 32, generator=gen).to(cuda_device)
+
+    def ref_idx():
+        zn, en = F.normalize(z.view(-1, 32).double(), dim=-1), F.normalize(vq.embedding.weight.detach(), dim=-1).double()
+        return (zn @ en.t()).argmax(1).view(2, 64)
+
+    assert torch.equal(vq(z)[2], ref_idx())
+    with torch.no_grad():
+        vq.embedding.weight.copy_(torch.randn(256, 32, generator=gen).to(cuda_device))      # bumps _version
+    assert torch.equal(vq(z)[2], ref_idx())
+    vq.load_state_dict({"embedding.weight": torch.randn(256, 32, generator=gen)})
+    assert torch.equal(vq(z)[2], ref_idx())
+    vq.embedding.weight.data.copy_(torch.randn(256, 32, generator=gen).to(cuda_device))     # bypasses the version counter
+    vq.invalidate()
+    assert torch.equal(vq(z)[2], ref_idx())
+    dec = vq.decode_from_indice(torch.arange(8, device=cuda_device).view(1, 8))
+    np.testing.assert_allclose(dec.view(-1, 32).cpu().numpy(), F.normalize(vq.embedding.weight.detach()[:8], dim=-1).cpu().numpy(), atol=1e-6)
+
+
 def test_empty_batch_matches_reference_conventions(cuda_device):
     """B = 0: the reference returns empty tensors and a nan loss (mean over zero elements); so do we (no kernel launch)."""
     cfg, sd, _ = seeded_vqgan("vit-tiny-test", 7)
