@@ -10,9 +10,9 @@ torch.distributed.run (one rank per GPU); work is batch-sharded (weak scaling: 2
 step) with a single NCCL all-reduce of the codebook-usage histogram + loss scalars at the end of the
 timed region.  Rank 0 prints ONE JSON line.
 
-`--impl reference` times the reference's CPU algorithm for the same path (the torch-CPU oracle port of
-the pure-Python/torch reference: same ATen operators, fp32, all host threads) on a bounded sample of the
-same workload (16 images per step; BASELINE configs[0] is the same pass at batch 4).
+`--impl reference` times the reference's own CPU implementation of the same path — the UNMODIFIED reference imported from
+baseline/_ref (or $PAINTMIND_REF, /root/reference) when present (`kind: "reference"`), else the torch-CPU oracle port of it
+(`kind: "port"`) — fp32, all host threads, on a bounded sample of the same workload: 4 images per step = BASELINE configs[0].
 """
 from __future__ import annotations
 
@@ -46,46 +46,75 @@ def _peaks():
 # CPU arm: the oracle port of the reference algorithm (test infrastructure, used here ONLY as the
 # thing being timed for the cpu_baseline / reference arm — never on the product path)
 # ------------------------------------------------------------------------------------------------
-CPU_SAMPLE = 16     # images per CPU pass (BASELINE configs[0] is the same pass at batch 4; 16 keeps all host cores busy)
+CPU_SAMPLE = 4      # images per CPU pass = BASELINE configs[0] (the reference's own CPU-runnable case: batch 4, fp32)
 
 
-def cpu_reference_images_per_s(sample_batch: int = CPU_SAMPLE, repeats: int = 1, warm: bool = True):
-    """Times encode+decode of `sample_batch` images with the torch-CPU oracle port (the same ATen CPU
-    operators the pure-Python reference dispatches to, all host threads, fp32, no autograd)."""
-    import torch
-    from oracle import paintmind_oracle_torch as OT
-    from paintmind_b200.config import ver2cfg
-    from paintmind_b200.utils import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = ver2cfg["vit-s-vqgan"]
-    sd = synthetic.make_vqgan_state_dict(cfg, seed=0)
-    x = synthetic.make_images(sample_batch, 256, seed=1000)
-    times = []
-    with torch.no_grad():
+class CpuArm:
+    """encode -> quantize -> decode on the host cores, fp32, all threads, no autograd: the UNMODIFIED reference
+    (`paintmind.stage1.VQModel.encode / decode`, stage1/vqmodel.py:21-30) when it can be imported — $PAINTMIND_REF,
+    baseline/_ref or /root/reference through oracle/ref_loader.py — kind "reference"; otherwise the torch-CPU oracle port of
+    the same ATen operators — kind "port"."""
+
+    def __init__(self):
+        import torch
+        from paintmind_b200.config import ver2cfg
+        from paintmind_b200.utils import synthetic
+        self.torch = torch
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.cfg = ver2cfg["vit-s-vqgan"]
+        self.sd = synthetic.make_vqgan_state_dict(self.cfg, seed=0)
+        self.synthetic = synthetic
+        self.model, self.kind, self.why_port = None, "port", None
+        try:
+            from oracle.ref_loader import find_reference, load_reference
+            pmref = load_reference()
+            from paintmind.stage1 import VQModel
+            m = VQModel(pmref.Config(self.cfg)).eval()
+            m.load_state_dict(self.sd, strict=True)
+            self.model, self.kind, self.where = m, "reference", find_reference()
+        except Exception as e:  # noqa: BLE001
+            self.why_port = f"{type(e).__name__}: {e}"
+            from oracle import paintmind_oracle_torch as OT
+            self.OT = OT
+
+    def describe(self):
+        if self.kind == "reference":
+            return f"unmodified reference VQModel.encode/decode imported from {self.where}, torch CPU fp32, {self.cores} threads"
+        return f"torch-CPU fp32 oracle port of the reference (reference not importable: {self.why_port}), {self.cores} threads"
+
+    def one_pass(self, x):
+        with self.torch.no_grad():
+            if self.model is not None:
+                z_q, loss, idx = self.model.encode(x)
+                return self.model.decode(z_q)
+            z_q, loss, idx = self.OT.vqmodel_encode(x, self.sd, self.cfg)
+            return self.OT.vqmodel_decode(z_q, self.sd, self.cfg)
+
+    def images_per_s(self, sample_batch=CPU_SAMPLE, repeats=1, warm=True):
+        x = self.synthetic.make_images(sample_batch, 256, seed=1000)
         if warm:
-            OT.vqmodel_encode(x[:1], sd, cfg)               # warm-up (thread pools, page-in)
+            self.one_pass(x[:1])                                # thread pools, page-in
+        times = []
         for _ in range(repeats):
             t0 = time.perf_counter()
-            z_q, loss, idx = OT.vqmodel_encode(x, sd, cfg)
-            rec = OT.vqmodel_decode(z_q, sd, cfg)
+            rec = self.one_pass(x)
             times.append(time.perf_counter() - t0)
-    assert bool(torch.isfinite(rec).all())
-    t = statistics.median(times)
-    return sample_batch / t, sum(times)
+        assert bool(self.torch.isfinite(rec).all())
+        return sample_batch / statistics.median(times), sum(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    arm = CpuArm()
     vals = []
     for _ in range(args.warmup):
-        cpu_reference_images_per_s(CPU_SAMPLE)              # untimed warm-up passes
+        arm.images_per_s(CPU_SAMPLE)                            # untimed warm-up passes
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
-        v, _ = cpu_reference_images_per_s(CPU_SAMPLE, warm=False)
+        v, _ = arm.images_per_s(CPU_SAMPLE, warm=False)
         vals.append(v)
     wall = time.perf_counter() - t_all0
     value = statistics.median(vals)
@@ -93,11 +122,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * CPU_SAMPLE / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": CPU_SAMPLE,
-                   "note": "bounded sample of the batch-256 workload: each step is one encode+decode pass over 16 images"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{CPU_SAMPLE} images per step x {args.steps} steps (torch-CPU fp32 oracle port of the "
-                                   f"reference: same ATen operators, {cores} threads)"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "tokens_per_image": 1024,
+                   "batch_per_step": CPU_SAMPLE,
+                   "note": f"bounded sample of the batch-{args.batch} workload: each step is one encode+decode pass over {CPU_SAMPLE} images "
+                           "(BASELINE configs[0], the reference's own CPU case); images/s does not depend on how many such passes make a batch"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                         "sample": f"{CPU_SAMPLE} images per step x {args.steps} steps ({arm.describe()})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
@@ -356,6 +386,29 @@ def run_ours(args):
                   "d2h_bytes_per_step": pxo_host.numel() + idx_host.numel() * 8 + 4,
                   "api": "VQModel.encode_pixels / decode_pixels (uint8 NHWC in and out)"}
 
+    # ---- parity at the benchmark's own configuration (outside every timed region): the batch the reference was run on
+    # for tests/golden/headline_vit_s_b256.npz (tests/make_golden_headline.py), through the same batch-B calls ----
+    parity = None
+    fx = ROOT / "tests" / "golden" / "headline_vit_s_b256.npz"
+    if rank == 0 and fx.exists() and B <= 256:
+        import numpy as np
+        gf = np.load(fx, allow_pickle=False)
+        xs = synthetic.make_images(int(gf["batch"]), 256, seed=int(gf["img_seed"]))[:B].to(dev)
+        _, loss_f, idx_f = model.encode(xs)
+        ref_idx = torch.from_numpy(gf["idx"][:B].astype(np.int64))
+        mism = idx_f.cpu() != ref_idx
+        gapf = torch.from_numpy(gf["gap"][:B].astype(np.float32))
+        rec_f = model.decode_from_indice(ref_idx.to(dev))
+        ps = int(gf["pix_stride"])
+        errf = (rec_f[:, :, ::ps, ::ps].cpu() - torch.from_numpy(gf["rec_sub"][:B].astype(np.float32))).abs()
+        parity = {"fixture": fx.name + " (unmodified reference, CPU fp32, same seeded weights and images)", "images": B,
+                  "idx_mismatch_frac": float(mism.float().mean()), "max_ref_gap_at_mismatch": float(gapf[mism].max()) if mism.any() else 0.0,
+                  "loss": float(loss_f), "ref_loss": float(gf["loss"]) if B == int(gf["batch"]) else None,
+                  "rec_max_abs_err": float(errf.max()), "rec_mean_abs_err": float(errf.mean())}
+        parity["ok"] = bool(parity["idx_mismatch_frac"] < 0.03 and parity["rec_max_abs_err"] < 0.061 and parity["rec_mean_abs_err"] < 0.006
+                            and (parity["ref_loss"] is None or abs(parity["loss"] - parity["ref_loss"]) < 0.02 * parity["ref_loss"]))
+        del xs, rec_f
+
     vq_rate = None
     if rank == 0:
         # secondary metric of BASELINE.json: VQ lookups/s on configs[1] (65,536 latents vs 8192 codes)
@@ -449,10 +502,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, secs = cpu_reference_images_per_s(2 * CPU_SAMPLE, repeats=4)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{2 * CPU_SAMPLE} images x 4 encode+decode passes (median) of the torch-CPU fp32 oracle port, "
-                         f"all host threads ({secs:.1f} s of CPU work)"}
+        arm = CpuArm()
+        v, secs = arm.images_per_s(CPU_SAMPLE, repeats=6)
+        cpu = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+               "sample": f"{CPU_SAMPLE} images (BASELINE configs[0]) x 6 encode+decode passes, median ({arm.describe()}; {secs:.1f} s of CPU work)"}
 
     if world > 1:
         dist.barrier()
@@ -469,7 +522,7 @@ def run_ours(args):
             "e2e_pixels": e2e_pixels,
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "vq_lookups_per_s": vq_rate, "maskgit": maskgit, "train_step": train,
-            "check": {"loss": global_loss, "codes_used": used_codes},
+            "check": {"loss": global_loss, "codes_used": used_codes, "parity_vs_reference": parity},
         }
         print(json.dumps(line), flush=True)
     return 0

@@ -1,9 +1,11 @@
-"""Import the real (unmodified) reference from a read-only mount — BUILD-CONTAINER ONLY.
+"""Import the real (unmodified) reference.
 
-Used by tests/make_golden.py to generate fixtures.  Nothing that runs on the GPU box imports
-this.  Recipe from SURVEY.md §8(c): two off-path reference modules (T5/CLIP embedders and the
-accelerate-based trainers) pull in packages that are absent here, so they are pre-registered as
-stubs in sys.modules; every on-path module is the reference's own code.
+Lookup order: $PAINTMIND_REF, `baseline/_ref` (the offline `pip install --no-deps --target baseline/_ref
+/root/reference` of DESIGN.md §5: git-ignored, travels to the GPU box with the snapshot), /root/reference (the read-only
+mount of the build container).  Used by tests/make_golden*.py to generate fixtures and by bench.py's CPU arms
+(`--impl reference`, `cpu_baseline`) as the thing being TIMED; nothing on the product path imports it.
+Two off-path reference modules (T5/CLIP embedders and the accelerate-based trainers) pull in packages that are absent
+here, so they are pre-registered as stubs in sys.modules; every on-path module is the reference's own code.
 """
 from __future__ import annotations
 
@@ -13,7 +15,8 @@ import types
 
 
 def find_reference():
-    for cand in (os.environ.get("PAINTMIND_REF"), "/root/reference"):
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("PAINTMIND_REF"), os.path.join(repo_root, "baseline", "_ref"), "/root/reference"):
         if cand and os.path.isdir(os.path.join(cand, "paintmind")):
             return cand
     return None

@@ -3,6 +3,8 @@
 #include "pm_common.cuh"
 #include "pm_kernels.h"
 
+#include <stdlib.h>
+
 using namespace pm;
 
 extern "C" {
@@ -79,6 +81,13 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
   p.o32 = a->o32;
   p.ldo32 = a->ldo32;
   if (p.o32 != nullptr && ((p.ldo32 % 4) != 0 || (reinterpret_cast<uintptr_t>(p.o32) & 15) != 0)) return PM_ERR_INVALID;
+  // PM_ATTN_IMPL=1: the round-1 kernel (8 softmax warps, pm_attn.cu); 2: the 16-softmax-warp kernel (pm_attn2.cu).  A/B aid.
+  static int impl = 0;
+  if (impl == 0) {
+    const char* env = getenv("PM_ATTN_IMPL");
+    impl = (env != nullptr && env[0] == '2') ? 2 : 1;
+  }
+  if (impl == 2) return pm_attn2_launch(p, static_cast<cudaStream_t>(stream));
   return pm_attn_launch(p, static_cast<cudaStream_t>(stream));
 }
 

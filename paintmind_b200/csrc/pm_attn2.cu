@@ -18,7 +18,9 @@
 //   * P_t V is issued in two halves (keys 0-63 as soon as the kh = 0 warps have stored their P columns);
 //   * the row sums meet once per item (shared memory) in the epilogue, where each thread also scales and stores its 32 of
 //     the 64 output columns.
-// 640 threads: warps 0-15 softmax (112 registers each after setmaxnreg), warp 16 TMA producer, warp 17 / 18 MMA issuers.
+// 640 threads: warps 0-15 softmax, warp 16 TMA producer, warp 17 / 18 MMA issuers.  Registers: 96 per thread at launch
+// (640 x 96 = 61,440 is the CTA's pool); setmaxnreg moves them to 104 per softmax thread and 64 per producer / issuer thread
+// (512 x 104 + 128 x 64 = 61,440 exactly — an increase beyond the pool blocks forever).
 // TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
 #include "pm_common.cuh"
 #include "pm_kernels.h"
@@ -135,7 +137,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 16) {
       // ===================================== TMA producer ======================================
       if (lane == 0) {
@@ -217,7 +219,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===================================== softmax warps =====================================
     const int t = warp >> 3;                       // Q tile 0 / 1
     const int kh = (warp >> 2) & 1;                // key half of every 128-key tile owned by this thread
@@ -270,9 +272,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           mo = fmaxf(m0, m1);
         }
         // ---- own 64 scores into registers ----
+        // The load address carries a data dependency on `mo` (0 unless the partner's scores are all NaN): the 64 registers of
+        // the partner's scores must be dead before the 64 own scores arrive — ptxas otherwise hoists these loads above the max
+        // tree, needs 128 + 40 registers and spills the score rows to local memory.
+        const uint32_t dep = (mo != mo) ? 1u : 0u;
         uint32_t s[2][32];
-        tmem_ld_x32(tS_own, s[0]);
-        tmem_ld_x32(tS_own + 32, s[1]);
+        tmem_ld_x32(tS_own + dep, s[0]);
+        tmem_ld_x32(tS_own + 32 + dep, s[1]);
         tmem_ld_wait();
         // every score this warp needs has been read: S_t may be overwritten by the next Q K^T (8 arrivals)
         tc_fence_before();
@@ -308,14 +314,15 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             // the kh = 0 warp rescales all 64 columns of O_t: the P_t V issuer only waits for kh = 0 before its first half
             mbar_wait_a(b_pv_done, (g - 1) & 1);     // O_t is still being accumulated by the previous step until this fires
             tc_fence_after();
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t r[32];
-              tmem_ld_x32(tO + cc * 32, r);
+            // 16 columns at a time: this rare path must not raise the register pressure of the loop (the score row stays live)
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t r[16];
+              tmem_ld_x16(tO + cc * 16, r);
               tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-              tmem_st_x32(tO + cc * 32, r);
+              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+              tmem_st_x16(tO + cc * 16, r);
             }
           }
         }

@@ -134,6 +134,7 @@ int pm_maskgit_random_mask_launch(const float* z, int64_t ldz, const float* nois
 int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, const long long* label, const float* mask,
                               float eps, float* row_loss, float* loss_out, double* sums_out, cudaStream_t stream);
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
+int pm_attn2_launch(const AttnParams& p, cudaStream_t stream);
 int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream);
 int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H,
                          int N, const float* lse, float scale, float* nds, float* nlse, int64_t delta_ld, cudaStream_t stream);

@@ -210,6 +210,13 @@ def run_blocks(blocks, x, st, B, N, ws, context_kv=None, ctx_len=0):
 class Stage1Engine:
     """Kernel sequencing for VQModel.encode / decode / decode_from_indice."""
 
+    def invalidate(self):
+        """Force a repack on the next call (after writes that bypass the version counter, e.g. `p.data.copy_`)."""
+        self._fp = None
+        m = self.model
+        if m is not None:
+            m.quantize.invalidate()
+
     def __init__(self, model=None, encoder=None, decoder=None):
         self._model = weakref.ref(model) if model is not None else None
         self._encoder = encoder if model is None else None
@@ -444,6 +451,13 @@ class Stage2Engine:
         self.ws = _Workspace()
         self._ctx_key = None
         self._ctx_kv = None
+        self._ctx_ref = None
+
+    def invalidate(self):
+        """Force a repack on the next call (after writes that bypass the version counter, e.g. `p.data.copy_`)."""
+        self._fp = None
+        self._ctx_key = self._ctx_kv = self._ctx_ref = None
+        self.__dict__.pop("_graph", None)
 
     @property
     def tr(self):
@@ -472,12 +486,16 @@ class Stage2Engine:
             self.w_logits, self.cs_logits, self.b_logits = fold_layernorm(tr.to_logits.weight.detach(), tr.to_logits.bias.detach(),
                                                                           tr.norm.weight.detach(), tr.norm.bias.detach())
         self._fp = fp
-        self._ctx_key = None
+        self._ctx_key = self._ctx_kv = self._ctx_ref = None
 
     def _context_kv(self, context):
-        """Per-layer K/V projections of the (fixed) text context; cached across MaskGIT steps."""
+        """Per-layer K/V projections of the (fixed) text context; cached across MaskGIT steps.
+
+        The cache entry keeps the context tensor itself: (data_ptr, _version) alone is not an identity — once a context is
+        freed, the caching allocator hands the next same-shaped one the same address with _version 0 and the previous
+        prompt's K/V would be served for it.  Holding the tensor pins its storage for as long as the key is live."""
         key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
-        if key == self._ctx_key:
+        if key == self._ctx_key and self._ctx_ref is context:
             return self._ctx_kv
         B, L, Dc = context.shape
         dev = context.device
@@ -493,7 +511,7 @@ class Stage2Engine:
             kv = torch.empty(B * L, 2 * blk.inner, device=dev, dtype=torch.bfloat16)
             ops.gemm(cb, blk.w_kv2, kv)
             kvs.append(kv)
-        self._ctx_key, self._ctx_kv = key, kvs
+        self._ctx_key, self._ctx_kv, self._ctx_ref = key, kvs, context
         return kvs
 
     def _run(self, zs, B, N, context):
@@ -548,6 +566,8 @@ def _graphed_forward_from_ids(self, ids, table, context=None):
     ckey = None if context is None else (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
     key = (tuple(ids.shape), ids.device.index, table.data_ptr(), table._version, ckey, self._fp)
     g = self.__dict__.get("_graph")
+    if g is not None and (g["context"] is not context or g["table"] is not table):
+        g = None          # same address, different tensor: the captured operands are only valid for the objects they were captured with
     if g is None or g["key"] != key:
         ids_static = ids.detach().to(torch.int64).contiguous().clone()
         cur = torch.cuda.current_stream(ids.device)
@@ -561,7 +581,12 @@ def _graphed_forward_from_ids(self, ids, table, context=None):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             logits = self.forward_from_ids(ids_static, table, context)
-        g = dict(key=key, graph=graph, ids=ids_static, logits=logits, context=context, table=table)   # keep the captured operands alive
+        # The graph has raw device addresses baked in.  Keep every tensor its kernels touch alive for as long as the graph is:
+        # the operands, the per-layer context K/V and ALL workspace buffers (the workspace evicts a buffer when the same
+        # name is requested with another shape — e.g. an eager call at another batch size — and the K/V cache is replaced
+        # by the next context; without these references a later replay would read and write freed memory).
+        g = dict(key=key, graph=graph, ids=ids_static, logits=logits, context=context, table=table,
+                 pinned=list(self.ws.bufs.values()) + list(self._ctx_kv or []))
         self.__dict__["_graph"] = g
     g["ids"].copy_(ids, non_blocking=True)
     g["graph"].replay()

@@ -66,8 +66,23 @@ class Pipeline(nn.Module):
         self._table = None
         self._table_fp = None
 
+    def _advance_rng(self):
+        """Philox key / counter of the next sampling call, drawn from torch's default generator: (torch.initial_seed(), one
+        31-bit draw).  Results are therefore a function of the torch RNG state — `torch.manual_seed(s)` before generate() /
+        random_masking() reproduces a run, as with the reference (whose own random stream differs: it draws 8192 uniforms
+        per token on the device)."""
+        self._rng_seed = torch.initial_seed()
+        self._rng_calls = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
     def from_pretrained(self, path):
-        return self.load_state_dict(torch.load(path))
+        """generate.py:73-75.  A reference Pipeline checkpoint also carries the frozen T5 encoder (`text_model.transformer.*`,
+        a registered submodule there).  The text encoder is out of scope here (`text_model` is a pluggable callable, by
+        default parameter-less): its keys are dropped unless the attached text model declares parameters of that name;
+        every other key is checked strictly."""
+        sd = torch.load(path, map_location="cpu")
+        own = set(self.state_dict().keys())
+        sd = {k: v for k, v in sd.items() if not (k.startswith("text_model.") and k not in own)}
+        return self.load_state_dict(sd, strict=True)
 
     # ---- stage-2 training FORWARD (generate.py:78-146; SURVEY.md §8f row 2) -------------------
     # Forward values only: like every other entry point of this package the result carries no autograd graph
@@ -92,9 +107,7 @@ class Pipeline(nn.Module):
             x2d = x2d.contiguous()
         mask = torch.empty(N, L, device=x.device, dtype=torch.float32)
         out = torch.empty(N * L, D, device=x.device, dtype=torch.float32)
-        if self._rng_seed is None:
-            self._rng_seed = torch.initial_seed()
-        self._rng_calls += 1
+        self._advance_rng()
         noise = None
         if _noise is not None:
             noise = _noise.to(device=x.device, dtype=torch.float32).contiguous()
@@ -192,9 +205,7 @@ class Pipeline(nn.Module):
         logits = fwd(ids, table, context)                                       # fp32 [B, N, V]
         pred_ids = torch.empty(B, N, device=dev, dtype=torch.int64)
         scores = torch.empty(B, N, device=dev, dtype=torch.float32)
-        if self._rng_seed is None:
-            self._rng_seed = torch.initial_seed()
-        self._rng_calls += 1
+        self._advance_rng()
         ops.maskgit_sample(logits.view(B * N, -1), topk=topk, temperature=temperature, ids=ids.view(-1),
                            pred_ids=pred_ids.view(-1), scores=scores.view(-1), mask_id=self.mask_token_id,
                            noise=None if _noise is None else _noise.reshape(B * N, -1),

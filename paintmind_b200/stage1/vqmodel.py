@@ -70,7 +70,36 @@ class VQModel(nn.Module):
         return _as_autocast(self.engine().decode_from_indice(indice))
 
     def from_pretrained(self, path):
-        return self.load_state_dict(torch.load(path))
+        """vqmodel.py:43-44.  `map_location="cpu"`: a checkpoint saved from another device (or a GPU this box does not
+        have) must load; load_state_dict copies into the parameters wherever they live."""
+        return self.load_state_dict(torch.load(path, map_location="cpu"))
+
+    def invalidate(self):
+        """Call after writing parameters through `.data` (EMA / weight surgery): such writes do not bump the version
+        counter the packed-weight caches are keyed on."""
+        if self._engine is not None:
+            self._engine.invalidate()
+        self.quantize.invalidate()
+        self.__dict__.pop("_train_engine", None)
+
+    # engines hold device buffers and a weak reference to THIS module: a copy / unpickled model builds its own
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_engine", "_train_engine"):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__["_engine"] = None
+        return new
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st.pop("_train_engine", None)
+        return st
 
     # -- pixels in / pixels out (SURVEY.md §8f row 3: the steps either side of the path) ----------
     @torch.no_grad()
@@ -128,6 +157,11 @@ class VQModel(nn.Module):
             with torch.cuda.graph(g), torch.no_grad():
                 out = body()
             state["graph"], state["out"], state["fp"] = g, out, _fingerprint(self)
+            # raw addresses are baked into the graph: pin every workspace buffer and codebook operand it addresses, so that a
+            # later eager call at another batch size (which makes the workspace drop same-named buffers) cannot free them
+            q = self.quantize
+            state["pinned"] = (list(self.engine().ws.bufs.values()) + [t for t in (q._prep or ())[1:]]
+                               + [t for t in (q._cand or ())[1:]])
 
         @torch.no_grad()
         def run(x=None):

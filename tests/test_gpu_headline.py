@@ -1,0 +1,89 @@
+"""Parity at the HEADLINE configuration (BASELINE configs[2]: vit-s-vqgan, ONE batch-256 call, M = 262,144 tokens) against the
+fixture tests/make_golden_headline.py produced from the unmodified reference (stage1/vqmodel.py:21-30).
+
+This is the shape bench.py times: 148-CTA persistent schedules with ~55 work items per CTA, the single-split VQ finish at
+M = 262,144 and the ~2 GB workspace are only exercised here.  Tolerances (stated):
+  * an index may differ from the fp32 reference only where the reference's top-2 distance gap is below 4 * ||zn_ours - zn_ref||
+    for that token (Lipschitz bound), checked per token on every 16th token (the fixture carries the reference latents of
+    those) and, for all 262,144 tokens, against 4 x the largest latent error seen on the sample (+25 %);
+  * mismatch rate below 3 % (the reference itself under bf16 autocast flips 3.25 %);
+  * reconstruction decoded from the reference's own code indices: max-abs / mean-abs error on a [::8, ::8] pixel sample and
+    per-image means, same bounds as the batch-2 test;
+  * loss within 2 % of the reference's, usage histogram consistent with the returned indices.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import check_weight_checksums, load_golden, seeded_vqgan
+from paintmind_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+
+REC_MAX, REC_MEAN = 0.06, 0.006
+
+
+def test_headline_batch256_vs_reference_golden(cuda_device):
+    import paintmind_b200 as pm
+    g = load_golden("headline_vit_s_b256.npz")
+    B, seed, img_seed = int(g["batch"]), int(g["seed"]), int(g["img_seed"])
+    ts, ps = int(g["tok_stride"]), int(g["pix_stride"])
+    cfg, sd, _ = seeded_vqgan("vit-s-vqgan", seed)
+    check_weight_checksums(g, sd)
+    x = synthetic.make_images(B, 256, seed=img_seed)
+    assert abs(float(x.double().sum()) - float(g["x_sum"])) < 1e-6 * max(1.0, abs(float(g["x_sum"]))), "seeded images differ from the fixture's"
+    model = pm.create_model(arch="vqgan", version="vit-s-vqgan", pretrained=False)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda_device).eval()
+    xd = x.to(cuda_device)
+
+    # ---- encode: ONE call at batch 256 ----
+    z_q, loss, idx = model.encode(xd)
+    assert idx.shape == (B, 1024) and z_q.shape == (B, 1024, 32)
+    idx_c = idx.cpu()
+    ref_idx = torch.from_numpy(g["idx"].astype(np.int64))
+    gap = torch.from_numpy(g["gap"].astype(np.float32))            # stored in fp16, rounded UP (never under-states a gap)
+    mism = idx_c != ref_idx
+    rate = mism.float().mean().item()
+
+    # per-token Lipschitz rule on the sampled tokens
+    z_pre = model.engine().latent(xd)[:, ::ts].cpu()
+    ref_z = torch.from_numpy(g["z_pre_sub"])
+    dz = (F.normalize(z_pre, dim=-1) - F.normalize(ref_z, dim=-1)).norm(dim=-1)          # [B, 1024 / ts]
+    ms, gs = mism[:, ::ts], gap[:, ::ts]
+    print(f"\n[headline b{B}] index mismatches vs fp32 reference: {int(mism.sum())}/{mism.numel()} ({100 * rate:.2f}%); "
+          f"latent error on the sample: mean {dz.mean():.4g} max {dz.max():.4g}; largest reference gap at a mismatch {gap[mism].max():.4g}")
+    assert dz.mean() < 0.02 and dz.max() < 0.08
+    assert torch.all(gs[ms] < 4.0 * dz[ms] + 1e-5), "an index differs where the reference gap exceeds the latent error bound"
+    # all tokens: rate, and no flip at a gap the sampled latent errors could not explain
+    assert rate < 0.03
+    assert gap[mism].max() < 4.0 * 1.25 * dz.max()
+    assert abs(loss.item() - float(g["loss"])) < 2e-2 * float(g["loss"])
+    hist = model.quantize._last_hist.cpu()
+    assert torch.equal(hist, torch.bincount(idx_c.view(-1), minlength=cfg["n_embed"]))
+    ref_hist = torch.zeros(cfg["n_embed"], dtype=torch.int64)
+    ref_hist[torch.from_numpy(g["hist_nonzero_bins"].astype(np.int64)) % 65536] = torch.from_numpy(g["hist_nonzero_counts"].astype(np.int64))
+    # usage histograms agree except for the flipped tokens (each flip moves one count between two bins)
+    assert (hist - ref_hist).abs().sum().item() <= 2 * int(mism.sum())
+    # z_q rows of matching indices are the reference's normalised code vectors
+    en = F.normalize(sd["quantize.embedding.weight"], dim=-1)
+    same = ~mism
+    np.testing.assert_allclose(z_q.cpu()[same][::97].numpy(), en[ref_idx[same]][::97].numpy(), atol=2e-6, rtol=0)
+
+    # ---- decode from the REFERENCE's code indices: ONE call at batch 256 ----
+    rec = model.decode_from_indice(ref_idx.to(cuda_device))
+    assert rec.shape == (B, 3, 256, 256) and rec.dtype == torch.float32 and rec.min() >= -1.0 and rec.max() <= 1.0
+    err = (rec[:, :, ::ps, ::ps].cpu() - torch.from_numpy(g["rec_sub"].astype(np.float32))).abs()
+    dmean = (rec.double().mean(dim=(1, 2, 3)).cpu() - torch.from_numpy(g["rec_mean"])).abs().max().item()
+    dabs = (rec.double().abs().mean(dim=(1, 2, 3)).cpu() - torch.from_numpy(g["rec_absmean"])).abs().max().item()
+    print(f"[headline b{B}] rec vs reference (same indices): max {err.max():.4g} mean {err.mean():.4g}; per-image mean off by {dmean:.3g}, abs-mean by {dabs:.3g}")
+    assert err.max() < REC_MAX + 1e-3 and err.mean() < REC_MEAN          # + fp16 storage of the sample
+    assert dmean < 2e-3 and dabs < 2e-3
+    # decode(z_q of our own encode) is what forward() returns; the reconstruction loop closes at this size too
+    rec2 = model.decode(z_q)
+    assert torch.isfinite(rec2).all() and rec2.abs().max() <= 1.0
+    # images whose 1024 indices all match the reference decode to the same pixels as the reference's indices did
+    clean = same.all(dim=1)
+    if clean.any():
+        assert (rec2[clean.to(cuda_device)] - rec[clean.to(cuda_device)]).abs().max() < 0.06

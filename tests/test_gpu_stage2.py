@@ -154,15 +154,53 @@ def test_pipeline_sample_step_vs_reference_golden(cuda_device, full_pipeline):
     torch.testing.assert_close(pipe._last_scores, scores_r, atol=2e-6, rtol=0)
     order = torch.argsort(-scores_r, dim=-1, stable=True)[:, :k]
     assert torch.equal(new_ids, ids_r.scatter(1, order, 8192))
-    # (2) agreement with the fp32 reference's discrete outputs (bf16 logit error can flip near-ties)
+    # (2) agreement with the fp32 reference's discrete outputs.  bf16 logits can only flip a decision where the REFERENCE
+    # itself is within the logit error of a tie; every disagreement is checked against the reference's own margins:
+    #   * the predicted id must be one of the reference's six largest logits of that token, and the reference's
+    #     gumbel-perturbed score of it (generate.py:40-46: logit / T - log(-log u), same injected uniforms) must be within
+    #     2 eps / T of the reference winner's, eps = the largest error of OUR logits on those six entries of that token;
+    #     the sixth candidate additionally needs the reference's 5th / 6th logits within 2 eps (the top-k filter, :33-37);
+    #   * a token whose prediction agrees may change its re-mask status (generate.py:175-179) only if the reference's
+    #     confidence score is within twice the largest score error (over agreeing tokens) of the reference's k-th score
+    #     (k-th +- m places when m tokens predict another id).
+    T = 0.75
     ref_pred = torch.from_numpy(g["pred_ids"].astype(np.int64))
-    agree = (pipe._last_pred_ids[0].cpu() == ref_pred).float().mean().item()
+    ours_pred = pipe._last_pred_ids[0].cpu()
+    top_val = torch.from_numpy(g["top6_val"])                                   # [N, 6] reference logits, descending
+    top_idx = torch.from_numpy(g["top6_idx"].astype(np.int64))
+    our_top = pipe._last_logits[0].cpu().gather(1, top_idx)
+    eps = (our_top - top_val).abs().max(dim=1).values                          # per-token logit error on the candidates
+    gum = -torch.log(-torch.log(u[0].cpu().gather(1, top_idx).clamp(min=1e-20)).clamp(min=1e-20))
+    ref_score = top_val / T + gum                                               # reference's perturbed candidate scores
+    ref_best = ref_score[:, :5].max(dim=1).values
+    is_masked = torch.from_numpy(g["ids_in"].astype(np.int64))[0] == 8192
+    diff = (ours_pred != ref_pred) & is_masked
+    agree = 1.0 - diff.float().sum().item() / max(int(is_masked.sum()), 1)
+    for tkn in torch.nonzero(diff).view(-1).tolist():
+        pos = torch.nonzero(top_idx[tkn] == ours_pred[tkn]).view(-1)
+        assert pos.numel() == 1, f"token {tkn}: predicted id {int(ours_pred[tkn])} is not among the reference's six largest logits"
+        j = int(pos[0])
+        assert ref_best[tkn] - ref_score[tkn, j] <= 2 * eps[tkn] / T + 1e-5, f"token {tkn}: not a reference near-tie"
+        if j == 5:
+            assert top_val[tkn, 4] - top_val[tkn, 5] <= 2 * eps[tkn] + 1e-6, f"token {tkn}: 6th logit is not within reach of the top-5 filter"
     ref_new = torch.from_numpy(g["new_ids"].astype(np.int64))
-    mask_agree = ((new_ids[0].cpu() == 8192) == (ref_new == 8192)).float().mean().item()
-    print(f"pred_ids agreement with fp32 reference: {100 * agree:.2f}%; re-mask set agreement: {100 * mask_agree:.2f}%")
-    assert agree > 0.85 and mask_agree > 0.9
-    # every disagreement must be a near-tie in the reference: the reference's own margin between its 5th and 6th
-    # logit, or between gumbel-perturbed candidates, is within the logit error bound
+    ref_scores = torch.from_numpy(g["scores"])
+    our_scores = pipe._last_scores[0].cpu()
+    same_pred = is_masked & ~diff
+    s_err = (our_scores - ref_scores)[same_pred].abs().max().item()
+    # tokens with another prediction have another confidence score and may cross the k-th place: with m of them the boundary
+    # moves by at most m ranks, so an agreeing token may flip only between the reference's (k-m)-th and (k+m+1)-th scores
+    m = int(diff.sum())
+    srt = ref_scores.sort(descending=True).values
+    hi = srt[max(k - 1 - m, 0)].item() + 2 * s_err + 1e-6
+    lo = srt[min(k + m, srt.numel() - 1)].item() - 2 * s_err - 1e-6
+    mask_diff = (new_ids[0].cpu() == 8192) != (ref_new == 8192)
+    mask_agree = 1.0 - mask_diff.float().mean().item()
+    bad = mask_diff & same_pred & ((ref_scores > hi) | (ref_scores < lo))
+    print(f"pred_ids agreement with fp32 reference: {100 * agree:.2f}% of masked tokens (every disagreement a reference near-tie, "
+          f"max candidate logit error {eps.max():.4g}); re-mask set agreement: {100 * mask_agree:.2f}% (score error {s_err:.3g})")
+    assert not bad.any(), f"{int(bad.sum())} tokens changed re-mask status away from the reference's k-th score"
+    assert agree > 0.9 and mask_agree > 0.9          # sanity floor; the margin checks above are the criterion
     # (3) decode of the predicted ids is the stage-1 decoder (already covered); same-pred pixels agree
     if agree == 1.0:
         assert (img[0, :, ::4, ::4].cpu() - torch.from_numpy(g["img_sub"])).abs().max() < 0.06
@@ -187,7 +225,7 @@ def test_pipeline_generate_cuda_graph_equals_eager(cuda_device, full_pipeline):
         res = []
         for text_seed in (1, 2):
             text = torch.randn(2, 77, 1024, generator=torch.Generator().manual_seed(text_seed)).to(cuda_device)
-            pipe._rng_seed, pipe._rng_calls = 99, 0
+            torch.manual_seed(99)              # the sampling noise is keyed on the torch generator state
             res.append(pipe.generate(text, timesteps=3, temperature=1.0, topk=5, save_interval=3)[0])
         outs[mode] = res
     pipe.cuda_graph = None

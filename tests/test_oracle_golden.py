@@ -87,3 +87,28 @@ def test_torch_oracle_stage1_tiny():
 
 def test_torch_oracle_stage1_vit_s():
     _run_stage1_torch("stage1_vit_s.npz")
+
+
+def test_oracle_headline_fixture_sample():
+    """Two of the 256 images of the batch-256 headline fixture (tests/make_golden_headline.py) through the numpy oracle:
+    pins the fixture the GPU test at the BASELINE configs[2] size compares against (tests/test_gpu_headline.py)."""
+    g = load_golden("headline_vit_s_b256.npz")
+    B, seed, img_seed = int(g["batch"]), int(g["seed"]), int(g["img_seed"])
+    ts, ps = int(g["tok_stride"]), int(g["pix_stride"])
+    cfg, sd_t, sd = seeded_vqgan("vit-s-vqgan", seed)
+    check_weight_checksums(g, sd_t)
+    x = synthetic.make_images(B, 256, seed=img_seed)
+    assert abs(float(x.double().sum()) - float(g["x_sum"])) < 1e-6 * max(1.0, abs(float(g["x_sum"])))
+    pick = [0, B - 1]
+    z_pre = O.vqmodel_latent(x[pick].numpy(), sd, cfg)
+    np.testing.assert_allclose(z_pre[:, ::ts], g["z_pre_sub"][pick], atol=2e-4, rtol=0)
+    z_q, loss, idx = O.vq_forward(z_pre, sd["quantize.embedding.weight"], cfg["beta"])
+    ref_idx = g["idx"][pick].astype(np.int64)
+    mism = idx != ref_idx
+    assert mism.mean() <= 0.002 and np.all(g["gap"][pick][mism].astype(np.float32) < 1e-4)
+    gap = O.vq_top2_gap(z_pre.reshape(-1, 32), sd["quantize.embedding.weight"]).reshape(2, -1)
+    np.testing.assert_allclose(gap, g["gap"][pick].astype(np.float32), atol=3e-6, rtol=1e-3)      # fp16 storage, rounded up
+    zq_ref = O.vq_decode_from_indice(ref_idx.reshape(-1), sd["quantize.embedding.weight"]).reshape(2, -1, 32)
+    rec = O.vqmodel_decode(zq_ref, sd, cfg)
+    np.testing.assert_allclose(rec[:, :, ::ps, ::ps], g["rec_sub"][pick].astype(np.float32), atol=1.5e-3, rtol=0)   # fp16 sample
+    np.testing.assert_allclose(rec.mean(axis=(1, 2, 3), dtype=np.float64), g["rec_mean"][pick], atol=2e-5)
