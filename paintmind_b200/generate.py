@@ -218,19 +218,40 @@ class Pipeline(nn.Module):
         return ids, img
 
     @torch.no_grad()
-    def generate(self, text, timesteps=18, temperature=1.0, topk=5, save_interval=2):
-        """MaskGIT iterative decoding (generate.py:183-198) -> list of CPU image tensors."""
+    def generate(self, text, timesteps=18, temperature=1.0, topk=5, save_interval=2, decode_every_step=False):
+        """MaskGIT iterative decoding (generate.py:183-198) -> list of CPU image tensors (one per kept step).
+
+        Two departures from the reference's loop, neither changes a returned value:
+          * the ViT decoder only runs on the steps whose image is kept (`step % save_interval == 0`); the reference decodes
+            every step and drops the rest (generate.py:193-196).  `decode_every_step=True` restores that (parity tests);
+          * kept images are staged on the device and leave through pinned host buffers on a side stream, with ONE
+            synchronisation after the last step; the reference's `img.cpu()` inside the loop (generate.py:196) blocks the
+            host, and with it the launch-bound small-batch loop, once per kept step."""
         dev = self.mask_token.device
         B = len(text)
-        imgs = []
         context = self._embed_text(text, dev)
         ids = torch.full((B, self.num_tokens), self.mask_token_id, dtype=torch.long, device=dev)
+        main = torch.cuda.current_stream(dev)
+        side = self.__dict__.get("_d2h_stream")
+        if side is None or side.device != dev:
+            side = torch.cuda.Stream(device=dev)
+            self.__dict__["_d2h_stream"] = side
+        imgs = []
         for step in range(timesteps):
             progress = (step + 1) / timesteps
             masked_r = mask_schedule(progress)
             cur_temp = temperature * (1 - step / timesteps)
             keep = (step % save_interval == 0)
-            ids, img = self.sample(ids, mask_ratio=masked_r, text=context, topk=topk, temperature=cur_temp, decode=keep)
+            ids, img = self.sample(ids, mask_ratio=masked_r, text=context, topk=topk, temperature=cur_temp,
+                                   decode=keep or decode_every_step)
             if keep:
-                imgs.append(img.cpu())
+                host = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    host.copy_(img, non_blocking=True)
+                img.record_stream(side)
+                imgs.append(host)
+        side.synchronize()
         return imgs

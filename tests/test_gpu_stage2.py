@@ -158,8 +158,9 @@ def test_pipeline_sample_step_vs_reference_golden(cuda_device, full_pipeline):
     # itself is within the logit error of a tie; every disagreement is checked against the reference's own margins:
     #   * the predicted id must be one of the reference's six largest logits of that token, and the reference's
     #     gumbel-perturbed score of it (generate.py:40-46: logit / T - log(-log u), same injected uniforms) must be within
-    #     2 eps / T of the reference winner's, eps = the largest error of OUR logits on those six entries of that token;
-    #     the sixth candidate additionally needs the reference's 5th / 6th logits within 2 eps (the top-k filter, :33-37);
+    #     2 eps / T of the best score in the candidate set, eps = the largest error of OUR logits on those six entries of that
+    #     token; the candidate set is the reference's top five, or — only when the reference's 5th / 6th logits are within
+    #     2 eps (the top-k filter, :33-37) — the set with the 6th in place of the 5th;
     #   * a token whose prediction agrees may change its re-mask status (generate.py:175-179) only if the reference's
     #     confidence score is within twice the largest score error (over agreeing tokens) of the reference's k-th score
     #     (k-th +- m places when m tokens predict another id).
@@ -170,19 +171,27 @@ def test_pipeline_sample_step_vs_reference_golden(cuda_device, full_pipeline):
     top_idx = torch.from_numpy(g["top6_idx"].astype(np.int64))
     our_top = pipe._last_logits[0].cpu().gather(1, top_idx)
     eps = (our_top - top_val).abs().max(dim=1).values                          # per-token logit error on the candidates
-    gum = -torch.log(-torch.log(u[0].cpu().gather(1, top_idx).clamp(min=1e-20)).clamp(min=1e-20))
+    lg = lambda t: torch.log(t.clamp(min=1e-20))  # noqa: E731   (generate.py:40-41)
+    gum = -lg(-lg(u[0].cpu().gather(1, top_idx)))
     ref_score = top_val / T + gum                                               # reference's perturbed candidate scores
     ref_best = ref_score[:, :5].max(dim=1).values
     is_masked = torch.from_numpy(g["ids_in"].astype(np.int64))[0] == 8192
     diff = (ours_pred != ref_pred) & is_masked
     agree = 1.0 - diff.float().sum().item() / max(int(is_masked.sum()), 1)
+    boundary_flips = 0
     for tkn in torch.nonzero(diff).view(-1).tolist():
         pos = torch.nonzero(top_idx[tkn] == ours_pred[tkn]).view(-1)
         assert pos.numel() == 1, f"token {tkn}: predicted id {int(ours_pred[tkn])} is not among the reference's six largest logits"
         j = int(pos[0])
-        assert ref_best[tkn] - ref_score[tkn, j] <= 2 * eps[tkn] / T + 1e-5, f"token {tkn}: not a reference near-tie"
-        if j == 5:
-            assert top_val[tkn, 4] - top_val[tkn, 5] <= 2 * eps[tkn] + 1e-6, f"token {tkn}: 6th logit is not within reach of the top-5 filter"
+        # candidate sets the top-5 filter may produce within the logit error: the reference's own, and — only if its 5th and
+        # 6th logits are within 2 eps — the one with the 6th in place of the 5th (the reference winner itself may drop out)
+        sets = [[0, 1, 2, 3, 4]]
+        if top_val[tkn, 4] - top_val[tkn, 5] <= 2 * eps[tkn] + 1e-6:
+            sets.append([0, 1, 2, 3, 5])
+        ok = any(j in c and ref_score[tkn, c].max() - ref_score[tkn, j] <= 2 * eps[tkn] / T + 1e-5 for c in sets)
+        assert ok, (f"token {tkn}: not a reference near-tie (candidate {j}, reference scores {ref_score[tkn].tolist()}, "
+                    f"5th-6th logit gap {float(top_val[tkn, 4] - top_val[tkn, 5]):.4g}, eps {float(eps[tkn]):.4g})")
+        boundary_flips += int(len(sets) == 2)
     ref_new = torch.from_numpy(g["new_ids"].astype(np.int64))
     ref_scores = torch.from_numpy(g["scores"])
     our_scores = pipe._last_scores[0].cpu()
@@ -212,6 +221,27 @@ def test_pipeline_generate_runs_schedule(cuda_device, full_pipeline):
     imgs = pipe.generate(["a", "b"], timesteps=3, temperature=1.0, topk=5, save_interval=2)
     assert len(imgs) == 2 and all(i.device.type == "cpu" and tuple(i.shape) == (2, 3, 256, 256) for i in imgs)
     assert all(float(i.min()) >= -1 and float(i.max()) <= 1 for i in imgs)
+
+
+def test_pipeline_generate_lazy_decode_equals_per_step_decode(cuda_device, full_pipeline):
+    """generate() decodes only the kept steps and stages their images on the device (one synchronisation at the end);
+    the reference decodes every step and copies inside the loop (generate.py:193-196).  Same images, bit for bit."""
+    pipe = full_pipeline
+    text = torch.randn(2, 77, 1024, generator=torch.Generator().manual_seed(11)).to(cuda_device)
+    res = []
+    for every in (False, True):
+        torch.manual_seed(7)
+        res.append(pipe.generate(text, timesteps=5, temperature=1.0, topk=5, save_interval=2, decode_every_step=every))
+    assert len(res[0]) == len(res[1]) == 3
+    for a, b in zip(*res):
+        assert a.device.type == "cpu" and a.is_pinned() and tuple(a.shape) == (2, 3, 256, 256)
+        assert torch.equal(a, b)
+    # and equal to decoding the ids the sampler produced (eager, blocking copy)
+    torch.manual_seed(7)
+    ids = torch.full((2, pipe.num_tokens), pipe.mask_token_id, dtype=torch.long, device=cuda_device)
+    from paintmind_b200.generate import mask_schedule
+    ids, img0 = pipe.sample(ids, mask_ratio=mask_schedule(1 / 5), text=text, topk=5, temperature=1.0, decode=True)
+    assert torch.equal(img0.cpu(), res[0][0])
 
 
 def test_pipeline_generate_cuda_graph_equals_eager(cuda_device, full_pipeline):
