@@ -405,7 +405,7 @@ def run_ours(args):
                   "idx_mismatch_frac": float(mism.float().mean()), "max_ref_gap_at_mismatch": float(gapf[mism].max()) if mism.any() else 0.0,
                   "loss": float(loss_f), "ref_loss": float(gf["loss"]) if B == int(gf["batch"]) else None,
                   "rec_max_abs_err": float(errf.max()), "rec_mean_abs_err": float(errf.mean())}
-        parity["ok"] = bool(parity["idx_mismatch_frac"] < 0.03 and parity["rec_max_abs_err"] < 0.061 and parity["rec_mean_abs_err"] < 0.006
+        parity["ok"] = bool(parity["idx_mismatch_frac"] < 0.03 and parity["rec_max_abs_err"] < 0.045 and parity["rec_mean_abs_err"] < 0.0045
                             and (parity["ref_loss"] is None or abs(parity["loss"] - parity["ref_loss"]) < 0.02 * parity["ref_loss"]))
         del xs, rec_f
 

@@ -7,8 +7,8 @@ M = 262,144 and the ~2 GB workspace are only exercised here.  Tolerances (stated
     for that token (Lipschitz bound), checked per token on every 16th token (the fixture carries the reference latents of
     those) and, for all 262,144 tokens, against 4 x the largest latent error seen on the sample (+25 %);
   * mismatch rate below 3 % (the reference itself under bf16 autocast flips 3.25 %, SURVEY.md §7.3);
-  * reconstruction decoded from the reference's own code indices: max-abs / mean-abs error on a [::8, ::8] pixel sample and
-    per-image means, same bounds as the batch-2 test;
+  * reconstruction decoded from the reference's own code indices: max-abs <= 0.045 / mean-abs <= 0.0045 on a [::8, ::8] pixel
+    sample (measured 0.0354 / 0.00359), per-image means within 2e-3;
   * loss within 2 % of the reference's, usage histogram consistent with the returned indices.
 """
 import numpy as np
@@ -21,7 +21,7 @@ from paintmind_b200.utils import synthetic
 
 pytestmark = pytest.mark.gpu
 
-REC_MAX, REC_MEAN = 0.06, 0.006
+REC_MAX, REC_MEAN = 0.045, 0.0045       # measured at batch 256: 0.0354 / 0.00359 (bf16 residual stream, see test_gpu_stage1.py)
 
 
 def test_headline_batch256_vs_reference_golden(cuda_device):
