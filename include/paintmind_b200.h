@@ -164,6 +164,7 @@ int pm_split_rows32(const float* src, int64_t ld, int32_t M, void* out_split, vo
  *   pm_patchify8_u8 : the same im2col fed from decoded pixels, uint8 NHWC [B, H, W, 3] (8-byte aligned), with the
  *                  reference's ingest transform fused (utils/transform.py:17-18: ToTensor u/255, Normalize
  *                  (t-0.5)/0.5, evaluated in fp32 exactly as torchvision does) — SURVEY.md §8f row 3.
+ *                  W <= 256 (one patch row of the image per block iteration; the reference models are 256 x 256).
  */
 /* pm_cast_f32_bf16 : fp32 -> bf16 (n % 8 == 0); the text context entering cross-attention k/v (transformer.py:84-86). */
 int pm_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -47,38 +47,62 @@ __device__ __forceinline__ float norm_u8(uint32_t u) {
 
 // The 256 possible results are tabulated once per block (bf16 bits in shared memory): the two IEEE divisions per
 // byte made the first version compute-bound (2.2 TB/s); with the table the kernel is a byte shuffle.
+//
+// Round 2: one block iteration = one ROW OF PATCHES (8 image rows x W pixels in, gw patch rows of 384 B out — contiguous in
+// `out`).  Thread (y, tw) converts 8 pixels into three 16-byte chunks as before, but drops them into a shared-memory image of
+// the output (patch pitch padded to 400 B: conflict-free 16-byte stores); the block then streams that image out with
+// consecutive threads writing consecutive 16-byte chunks.  The first version wrote its chunks straight to global memory,
+// 16 bytes every 384: half-filled sectors, 2.6 TB/s (40 % of the copy peak, profiles/r01_membound.txt).
+constexpr int PU8_PITCH = 400;                 // bytes per patch in the staging image (384 + 16)
+
 __global__ void __launch_bounds__(256)
 patchify8_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
   __shared__ uint16_t lut[256];
+  extern __shared__ __align__(16) uint8_t stage[];          // [gw][PU8_PITCH]
   {
     const __nv_bfloat16 h = __float2bfloat16_rn(norm_u8(threadIdx.x));
     lut[threadIdx.x] = *reinterpret_cast<const uint16_t*>(&h);
   }
   __syncthreads();
   const int gw = W >> 3, gh = H >> 3;
-  const long long total = static_cast<long long>(B) * H * gw;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int tw = static_cast<int>(t % gw);
-    const long long r = t / gw;
-    const int y = static_cast<int>(r % H);
-    const int b = static_cast<int>(r / H);
-    const uint2* src = reinterpret_cast<const uint2*>(img + ((static_cast<size_t>(b) * H + y) * W + tw * 8) * 3);
-    const uint2 w0 = __ldcs(src), w1 = __ldcs(src + 1), w2 = __ldcs(src + 2);
-    const uint32_t wd[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
-    uint32_t v[3][8];
+  const int work = gw * 8;                                   // (y, tw) pairs of one patch row
+  const int chunks = gw * 24;                                // 16-byte chunks of its output
+  const long long n_rows = static_cast<long long>(B) * gh;
+  // (y, tw) of this thread within a patch row; the loads of the NEXT patch row are issued before this one is streamed out
+  const bool active = static_cast<int>(threadIdx.x) < work;       // gw <= 32 (W <= 256): one (y, tw) pair per thread
+  const int tw0 = threadIdx.x % gw, kh0 = threadIdx.x / gw;
+  auto load = [&](long long pr, uint2& w0, uint2& w1, uint2& w2) {
+    const int th = static_cast<int>(pr % gh);
+    const int b = static_cast<int>(pr / gh);
+    const uint2* src = reinterpret_cast<const uint2*>(img + ((static_cast<size_t>(b) * H + th * 8 + kh0) * W + tw0 * 8) * 3);
+    w0 = __ldcs(src); w1 = __ldcs(src + 1); w2 = __ldcs(src + 2);
+  };
+  uint2 w0 = make_uint2(0u, 0u), w1 = w0, w2 = w0;
+  long long pr = blockIdx.x;
+  if (pr < n_rows && active) load(pr, w0, w1, w2);
+  for (; pr < n_rows; pr += gridDim.x) {
+    if (active) {
+      const uint32_t wd[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+      uint32_t v[3][8];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) v[i % 3][i / 3] = lut[(wd[i >> 2] >> ((i & 3) * 8)) & 0xffu];
-    const int th = y >> 3, kh = y & 7;
-    const size_t row = (static_cast<size_t>(b) * gh + th) * gw + tw;
-    __nv_bfloat16* dst = out + row * 192 + kh * 8;
+      for (int i = 0; i < 24; ++i) v[i % 3][i / 3] = lut[(wd[i >> 2] >> ((i & 3) * 8)) & 0xffu];
+      uint8_t* dst = stage + tw0 * PU8_PITCH + kh0 * 16;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      uint4 o;
-      o.x = v[c][0] | (v[c][1] << 16); o.y = v[c][2] | (v[c][3] << 16);
-      o.z = v[c][4] | (v[c][5] << 16); o.w = v[c][6] | (v[c][7] << 16);
-      *reinterpret_cast<uint4*>(dst + c * 64) = o;
+      for (int c = 0; c < 3; ++c) {
+        uint4 o;
+        o.x = v[c][0] | (v[c][1] << 16); o.y = v[c][2] | (v[c][3] << 16);
+        o.z = v[c][4] | (v[c][5] << 16); o.w = v[c][6] | (v[c][7] << 16);
+        *reinterpret_cast<uint4*>(dst + c * 128) = o;
+      }
     }
+    __syncthreads();
+    if (pr + gridDim.x < n_rows && active) load(pr + gridDim.x, w0, w1, w2);
+    uint4* gdst = reinterpret_cast<uint4*>(out + static_cast<size_t>(pr) * gw * 192);
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+      const int tw = i / 24, ch = i - tw * 24;
+      __stcs(gdst + i, *reinterpret_cast<const uint4*>(stage + tw * PU8_PITCH + ch * 16));
+    }
+    __syncthreads();
   }
 }
 
@@ -92,56 +116,77 @@ constexpr int LN_MAX_VEC = 8;   // 8 x (32 lanes x 8 elts) = 2048 columns
 
 // NV = 16-byte vectors per lane actually needed (D <= NV * 256): the row lives in NV * 8 registers per lane, so
 // D = 512 compiles to a 2-vector kernel with ~4x the occupancy of the generic 8-vector one (measured: 1.9 -> TB/s).
+// Round 2: every warp handles TWO rows at once (2 NV 16-byte loads in flight per lane instead of NV): at D = 512 one row per
+// warp left the kernel at 4.0 TB/s, latency-bound on 32 bytes in flight per lane (profiles/r01_membound.txt).
 template <int MODE, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 2 ? 4 : 1)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int D, float eps,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int64_t ldy, float* __restrict__ stats) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const __nv_bfloat16* xr = x + static_cast<size_t>(warp) * ldx;
+  const int row0 = 2 * warp;
+  if (row0 >= M) return;
+  const bool two = row0 + 1 < M;
   const int nvec = D >> 3;                      // 16-byte vectors per row
-  float v[NV][8];
-  float sum = 0.0f;
+  float v[2][NV][8];
+  uint4 u[2][NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = i * 32 + lane;
-    if (vi < nvec) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
-      v[i][0] = bf16lo_to_f32(u.x); v[i][1] = bf16hi_to_f32(u.x);
-      v[i][2] = bf16lo_to_f32(u.y); v[i][3] = bf16hi_to_f32(u.y);
-      v[i][4] = bf16lo_to_f32(u.z); v[i][5] = bf16hi_to_f32(u.z);
-      v[i][6] = bf16lo_to_f32(u.w); v[i][7] = bf16hi_to_f32(u.w);
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) sum += v[i][k];
+    for (int i = 0; i < NV; ++i) {
+      const int vi = i * 32 + lane;
+      u[r][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (vi < nvec && (r == 0 || two)) u[r][i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row0 + r) * ldx + vi * 8);
     }
+  float sum[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[r][i][0] = bf16lo_to_f32(u[r][i].x); v[r][i][1] = bf16hi_to_f32(u[r][i].x);
+      v[r][i][2] = bf16lo_to_f32(u[r][i].y); v[r][i][3] = bf16hi_to_f32(u[r][i].y);
+      v[r][i][4] = bf16lo_to_f32(u[r][i].z); v[r][i][5] = bf16hi_to_f32(u[r][i].z);
+      v[r][i][6] = bf16lo_to_f32(u[r][i].w); v[r][i][7] = bf16hi_to_f32(u[r][i].w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum[r] += v[r][i][k];          // lanes beyond the row hold zeros
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+    sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
   }
+  float mean[2], rstd[2], sq[2] = {0.0f, 0.0f};
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / static_cast<float>(D);
-  float sq = 0.0f;
+  for (int r = 0; r < 2; ++r) {
+    mean[r] = sum[r] / static_cast<float>(D);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = i * 32 + lane;
-    if (vi < nvec) {
+    for (int i = 0; i < NV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float d = v[i][k] - mean;
-        sq = fmaf(d, d, sq);
+        for (int k = 0; k < 8; ++k) {
+          const float d = v[r][i][k] - mean[r];
+          sq[r] = fmaf(d, d, sq[r]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / static_cast<float>(D) + eps);
+  for (int o = 16; o > 0; o >>= 1) {
+    sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], o);
+    sq[1] += __shfl_xor_sync(0xffffffffu, sq[1], o);
+  }
+  rstd[0] = rsqrtf(sq[0] / static_cast<float>(D) + eps);
+  rstd[1] = rsqrtf(sq[1] / static_cast<float>(D) + eps);
   if (MODE == 0) {
-    if (lane == 0) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(warp)) = make_float2(mean, rstd);
+    if (lane == 0) {
+      *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0)) = make_float2(mean[0], rstd[0]);
+      if (two) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + 1)) = make_float2(mean[1], rstd[1]);
+    }
     return;
   }
-  __nv_bfloat16* yr = y + static_cast<size_t>(warp) * ldy;
-  float ysum = 0.0f;
-  float yv[NV][8];
+  float ysum[2] = {0.0f, 0.0f};
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = i * 32 + lane;
@@ -152,40 +197,55 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int D,
       const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
       const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      uint32_t pk[4];
 #pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        const float a0 = (v[i][k] - mean) * rstd * g[k] + bb[k];
-        const float a1 = (v[i][k + 1] - mean) * rstd * g[k + 1] + bb[k + 1];
-        pk[k >> 1] = pack_bf16x2(a0, a1);
-        // statistics of the ROUNDED output (what the next GEMM will actually read)
-        yv[i][k] = bf16lo_to_f32(pk[k >> 1]);
-        yv[i][k + 1] = bf16hi_to_f32(pk[k >> 1]);
-        ysum += yv[i][k] + yv[i][k + 1];
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          const float a0 = (v[r][i][k] - mean[r]) * rstd[r] * g[k] + bb[k];
+          const float a1 = (v[r][i][k + 1] - mean[r]) * rstd[r] * g[k + 1] + bb[k + 1];
+          pk[k >> 1] = pack_bf16x2(a0, a1);
+          // statistics of the ROUNDED output (what the next GEMM will actually read); v is reused to hold it
+          v[r][i][k] = bf16lo_to_f32(pk[k >> 1]);
+          v[r][i][k + 1] = bf16hi_to_f32(pk[k >> 1]);
+          ysum[r] += v[r][i][k] + v[r][i][k + 1];
+        }
+        *reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * ldy + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      *reinterpret_cast<uint4*>(yr + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
   if (stats != nullptr) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
-    const float ymean = ysum / static_cast<float>(D);
-    float ysq = 0.0f;
+    for (int o = 16; o > 0; o >>= 1) {
+      ysum[0] += __shfl_xor_sync(0xffffffffu, ysum[0], o);
+      ysum[1] += __shfl_xor_sync(0xffffffffu, ysum[1], o);
+    }
+    float ysq[2] = {0.0f, 0.0f};
+    const float ymean[2] = {ysum[0] / static_cast<float>(D), ysum[1] / static_cast<float>(D)};
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float d = yv[i][k] - ymean;
-          ysq = fmaf(d, d, ysq);
+      for (int i = 0; i < NV; ++i) {
+        const int vi = i * 32 + lane;
+        if (vi < nvec) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float d = v[r][i][k] - ymean[r];
+            ysq[r] = fmaf(d, d, ysq[r]);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ysq += __shfl_xor_sync(0xffffffffu, ysq, o);
-    if (lane == 0)
-      *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(warp)) = make_float2(ymean, rsqrtf(ysq / static_cast<float>(D) + eps));
+    for (int o = 16; o > 0; o >>= 1) {
+      ysq[0] += __shfl_xor_sync(0xffffffffu, ysq[0], o);
+      ysq[1] += __shfl_xor_sync(0xffffffffu, ysq[1], o);
+    }
+    if (lane == 0) {
+      *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0)) = make_float2(ymean[0], rsqrtf(ysq[0] / static_cast<float>(D) + eps));
+      if (two)
+        *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + 1)) = make_float2(ymean[1], rsqrtf(ysq[1] / static_cast<float>(D) + eps));
+    }
   }
 }
 
@@ -217,20 +277,21 @@ int pm_patchify_launch(const float* img, void* out, int B, int C, int H, int W, 
 int pm_patchify_u8_launch(const uint8_t* img, void* out, int B, int H, int W, cudaStream_t stream) {
   if (img == nullptr || out == nullptr || (H % 8) != 0 || (W % 8) != 0 || B <= 0) return PM_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(img) & 7) != 0) return PM_ERR_INVALID;
-  const long long total = static_cast<long long>(B) * H * (W / 8);
   const int threads = 256;                                        // == table size
-  long long blocks = (total + threads - 1) / threads;
-  const long long cap = static_cast<long long>(pm_num_sms()) * 32;   // grid-stride: amortise the table build
+  long long blocks = static_cast<long long>(B) * (H / 8);         // one patch row per block iteration
+  const long long cap = static_cast<long long>(pm_num_sms()) * 8; // grid-stride: amortise the table build
   if (blocks > cap) blocks = cap;
-  patchify8_u8_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, H, W);
+  const int smem = (W / 8) * PU8_PITCH;
+  if (W > 256) return PM_ERR_INVALID;                             // one (image row, patch) pair per thread of a 256-thread block
+  patchify8_u8_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, H, W);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <int NV>
 static void launch_ln(const void* x, int64_t ldx, int M, int D, float eps, const float* gamma, const float* beta, void* y,
                       int64_t ldy, float* stats, cudaStream_t stream) {
-  const int threads = 256;                       // 8 rows per block
-  const int blocks = (M + 7) / 8;
+  const int threads = 256;                       // 8 warps x 2 rows per block
+  const int blocks = (M + 15) / 16;
   if (y == nullptr)
     layernorm_kernel<0, NV><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, D, eps,
                                                             nullptr, nullptr, nullptr, 0, stats);
