@@ -267,8 +267,11 @@ def run_ours(args):
     hist_acc.zero_(); sse_acc.zero_()
 
     # ---- timed region 1: device-resident inputs (the `value`) ----
+    # Only the dominant kernel (attention, 16 launches per step) is bracketed by CUDA events inside the timed region — that is
+    # the live duration the `roofline` object is computed from; the per-kernel table comes from a separate untimed pass below
+    # (events around all ~90 launches of a step were inside the timed region in round 1).
     clocks = ClockSampler(local_rank)
-    ops.PROFILE = {}
+    ops.PROFILE, ops.PROFILE_ONLY = {}, {"attention"}
     ops.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -281,7 +284,7 @@ def run_ours(args):
     barrier()
     clk = clocks.stop()
     launches = ops.LAUNCHES
-    prof, ops.PROFILE = ops.PROFILE, None
+    prof_dom, ops.PROFILE, ops.PROFILE_ONLY = ops.PROFILE, None, None
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -291,7 +294,12 @@ def run_ours(args):
     global_loss = float(1.25 * sse_acc[0] / sse_acc[1])
     used_codes = int((hist_acc > 0).sum())
 
-    # per-kernel table -> dominant kernel for the roofline object
+    # per-kernel table (untimed pass, every launch bracketed by events) -> shares; dominant kernel's duration from the timed region
+    ops.PROFILE = {}
+    for _ in range(2):
+        step(x_dev)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
     peaks = _peaks()
     table = []
     for key, evs in prof.items():
@@ -300,7 +308,13 @@ def run_ours(args):
     table.sort(reverse=True)
     ktot = sum(r[0] for r in table)
     dom_t, dom_key, dom_n = table[0]
-    dom_ms = dom_t / dom_n
+    if dom_key in prof_dom:                 # live: events recorded inside timed region 1
+        evs = prof_dom[dom_key]
+        dom_ms = sum(s.elapsed_time(e) for s, e in evs) / len(evs)
+        dom_src = f"CUDA events around each of the {len(evs)} launches inside the timed region"
+    else:
+        dom_ms = dom_t / dom_n
+        dom_src = "CUDA events in the untimed profiling pass (kernel was not pre-selected for in-region timing)"
     achieved = op_flops(dom_key) / (dom_ms * 1e-3) / 1e12
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
@@ -309,7 +323,7 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "pm_" + "_".join(str(k) for k in dom_key), "achieved": achieved,
                 "peak": peaks["tf_sustained"], "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
                 "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
-                "share_of_step": dom_t / ktot, "avg_launch_ms": dom_ms,
+                "share_of_step": dom_t / ktot, "avg_launch_ms": dom_ms, "duration_source": dom_src,
                 "e2e_algorithmic_tflops": value / world * FLOP_PER_IMAGE / 1e12,
                 "e2e_frac_of_peak": value / world * FLOP_PER_IMAGE / 1e12 / peaks["tf_sustained"]}
     kernels = [{"kernel": "_".join(str(k) for k in key), "launches": n, "ms_total": round(tot, 3), "share": round(tot / ktot, 4),

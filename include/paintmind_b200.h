@@ -183,6 +183,16 @@ int pm_layernorm(const void* x, int64_t ldx, int32_t M, int32_t D, float eps, co
  *   pm_maskgit_remask : ids.scatter(1, scores.topk(k).indices, mask_id) per image (generate.py:175-179);
  *                       ties at the k-th score resolve to the lower token index.
  * ------------------------------------------------------------------------------------------- */
+/* Per-step scalars of the MaskGIT loop (generate.py:186-192: temperature * (1 - step / T), the number of tokens to re-mask,
+ * the noise key) in DEVICE memory, one entry per step.  When `step_tab` is given, the kernels read entry *step_idx instead of
+ * their by-value arguments, and pm_maskgit_remask_step — the last kernel of a step — advances *step_idx: one captured CUDA
+ * graph (gather -> transformer -> sample -> re-mask) then serves every step of generate(), including the RNG stream. */
+typedef struct pm_step_scalars {
+  float temperature;
+  int32_t k;              /* tokens to re-mask after this step */
+  uint64_t seed, offset;  /* Philox key / stream offset of this step's gumbel noise */
+} pm_step_scalars;
+
 typedef struct pm_maskgit_sample_args {
   const float* logits;
   const float* noise;     /* optional [M, V] uniforms in [0,1) */
@@ -194,10 +204,15 @@ typedef struct pm_maskgit_sample_args {
   uint64_t seed, offset;
   int32_t M, V, topk;
   float temperature;
+  const pm_step_scalars* step_tab; /* optional (with step_idx): temperature / seed / offset come from step_tab[*step_idx] */
+  const int32_t* step_idx;
 } pm_maskgit_sample_args;
 
 int pm_maskgit_sample(const pm_maskgit_sample_args* args, void* stream);
 int pm_maskgit_remask(const float* scores, int64_t* ids, int32_t B, int32_t N, int32_t k, int64_t mask_id, void* stream);
+/* pm_maskgit_remask with k = step_tab[*step_idx].k; afterwards *step_idx += 1 (`ticket`: one zero-initialised int32 of scratch) */
+int pm_maskgit_remask_step(const float* scores, int64_t* ids, int32_t B, int32_t N, int64_t mask_id, const pm_step_scalars* step_tab,
+                           int32_t* step_idx, int32_t* ticket, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage-2 training forward, the pieces around the transformer (generate.py:78-146):

@@ -71,6 +71,7 @@ class MaskgitSampleArgs(C.Structure):
         ("ld", C.c_int64), ("ld_noise", C.c_int64), ("mask_id", C.c_int64),
         ("seed", C.c_uint64), ("offset", C.c_uint64),
         ("M", C.c_int32), ("V", C.c_int32), ("topk", C.c_int32), ("temperature", C.c_float),
+        ("step_tab", C.c_void_p), ("step_idx", C.c_void_p),
     ]
 
 
@@ -123,6 +124,7 @@ EXPORTS = {
     "pm_cast_f32_bf16": [_p, _p, _i64, _p],
     "pm_maskgit_sample": [C.POINTER(MaskgitSampleArgs), _p],
     "pm_maskgit_remask": [_p, _p, _i32, _i32, _i32, _i64, _p],
+    "pm_maskgit_remask_step": [_p, _p, _i32, _i32, _i64, _p, _p, _p, _p],
     "pm_maskgit_random_mask": [_p, _i64, _p, C.c_uint64, C.c_uint64, _p, _i32, _i32, _i32, _p, _p, _p],
     "pm_ce_label_smooth": [_p, _i64, _i32, _i32, _p, _p, _f, _p, _p, _p, _p],
     # generator backward path

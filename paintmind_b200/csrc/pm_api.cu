@@ -215,11 +215,23 @@ int pm_maskgit_sample(const pm_maskgit_sample_args* a, void* stream) {
   p.ids = reinterpret_cast<long long*>(a->ids);
   p.pred_ids = reinterpret_cast<long long*>(a->pred_ids);
   p.scores = a->scores; p.mask_id = a->mask_id;
+  p.step_tab = reinterpret_cast<const StepScalars*>(a->step_tab);
+  p.step_idx = a->step_idx;
+  if (p.step_tab != nullptr && p.step_idx == nullptr) return PM_ERR_INVALID;
   return pm_maskgit_sample_launch(p, static_cast<cudaStream_t>(stream));
 }
 
 int pm_maskgit_remask(const float* scores, int64_t* ids, int32_t B, int32_t N, int32_t k, int64_t mask_id, void* stream) {
-  return pm_maskgit_remask_launch(scores, reinterpret_cast<long long*>(ids), B, N, k, mask_id, static_cast<cudaStream_t>(stream));
+  return pm_maskgit_remask_launch(scores, reinterpret_cast<long long*>(ids), B, N, k, mask_id, nullptr, nullptr, nullptr,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int pm_maskgit_remask_step(const float* scores, int64_t* ids, int32_t B, int32_t N, int64_t mask_id, const pm_step_scalars* step_tab,
+                           int32_t* step_idx, int32_t* ticket, void* stream) {
+  static_assert(sizeof(pm_step_scalars) == sizeof(StepScalars), "pm_step_scalars layout");
+  if (step_tab == nullptr) return PM_ERR_INVALID;
+  return pm_maskgit_remask_launch(scores, reinterpret_cast<long long*>(ids), B, N, 0, mask_id,
+                                  reinterpret_cast<const StepScalars*>(step_tab), step_idx, ticket, static_cast<cudaStream_t>(stream));
 }
 
 int pm_maskgit_random_mask(const float* z, int64_t ldz, const float* noise, uint64_t seed, uint64_t offset,

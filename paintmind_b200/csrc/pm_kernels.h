@@ -93,6 +93,13 @@ struct VqParams {
   unsigned long long* hist;        // [n_e] += usage counts, optional
 };
 
+// per-step scalars of the MaskGIT loop in device memory (== pm_step_scalars of the C-ABI header)
+struct StepScalars {
+  float temperature;
+  int k;
+  unsigned long long seed, offset;
+};
+
 struct MaskgitParams {
   const float* logits;             // [M, V] fp32, row pitch ld
   int64_t ld;
@@ -105,6 +112,8 @@ struct MaskgitParams {
   long long* pred_ids;             // [M] out
   float* scores;                   // [M] out: 1 - p(pred) at masked positions, -1e5 elsewhere
   long long mask_id;
+  const StepScalars* step_tab;     // optional: temperature / seed / offset are read from step_tab[*step_idx] (CUDA-graph replay)
+  const int* step_idx;
 };
 
 int pm_num_sms();
@@ -127,7 +136,8 @@ inline int pm_ensure_dyn_smem(Kern kern, int bytes, bool* done) {
 }
 int pm_cast_launch(const float* src, void* dst, long long n, cudaStream_t stream);
 int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream);
-int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, cudaStream_t stream);
+int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, const StepScalars* step_tab,
+                             int* step_idx, int* ticket, cudaStream_t stream);
 int pm_maskgit_random_mask_launch(const float* z, int64_t ldz, const float* noise, unsigned long long seed,
                                   unsigned long long offset, const float* mask_token, int B, int N, int len_keep,
                                   float* mask, float* x_out, cudaStream_t stream);

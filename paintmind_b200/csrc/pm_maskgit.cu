@@ -72,7 +72,15 @@ struct TopList {
 
 template <int KMAX>
 __global__ void __launch_bounds__(256)
-maskgit_sample_kernel(const MaskgitParams p) {
+maskgit_sample_kernel(const MaskgitParams p_in) {
+  // per-step scalars from device memory when the step runs inside a CUDA graph (see pm_step_scalars in the C-ABI header)
+  MaskgitParams p = p_in;
+  if (p_in.step_tab != nullptr) {
+    const StepScalars sc = p_in.step_tab[*p_in.step_idx];
+    p.temperature = sc.temperature;
+    p.seed = sc.seed;
+    p.offset = sc.offset;
+  }
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= p.M) return;
@@ -176,7 +184,15 @@ constexpr int MG_CAND = 128;     // candidate capacity per row (expected: k .. ~
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-maskgit_sample_smem_kernel(const MaskgitParams p) {
+maskgit_sample_smem_kernel(const MaskgitParams p_in) {
+  // per-step scalars from device memory when the step runs inside a CUDA graph (see pm_step_scalars in the C-ABI header)
+  MaskgitParams p = p_in;
+  if (p_in.step_tab != nullptr) {
+    const StepScalars sc = p_in.step_tab[*p_in.step_idx];
+    p.temperature = sc.temperature;
+    p.seed = sc.seed;
+    p.offset = sc.offset;
+  }
   extern __shared__ __align__(128) uint8_t mg_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_bytes = p.V * 4;
@@ -373,7 +389,15 @@ constexpr int MGB_WARPS = 4;
 constexpr int MGB_CAND = 64;      // per warp
 
 __global__ void __launch_bounds__(MGB_WARPS * 32)
-maskgit_sample_block_kernel(const MaskgitParams p) {
+maskgit_sample_block_kernel(const MaskgitParams p_in) {
+  // per-step scalars from device memory when the step runs inside a CUDA graph (see pm_step_scalars in the C-ABI header)
+  MaskgitParams p = p_in;
+  if (p_in.step_tab != nullptr) {
+    const StepScalars sc = p_in.step_tab[*p_in.step_idx];
+    p.temperature = sc.temperature;
+    p.seed = sc.seed;
+    p.offset = sc.offset;
+  }
   extern __shared__ __align__(128) uint8_t mg_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_bytes = p.V * 4;
@@ -607,8 +631,10 @@ maskgit_sample_block_kernel(const MaskgitParams p) {
 // rank_i = #{j : s_j > s_i  or (s_j == s_i and j < i)};  token i is re-masked iff rank_i < k.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-maskgit_remask_kernel(const float* __restrict__ scores, long long* __restrict__ ids, int N, int k, long long mask_id) {
+maskgit_remask_kernel(const float* __restrict__ scores, long long* __restrict__ ids, int N, int k, long long mask_id,
+                      const StepScalars* __restrict__ step_tab, int* __restrict__ step_idx, int* __restrict__ ticket) {
   extern __shared__ float sm_scores[];
+  if (step_tab != nullptr) k = step_tab[*step_idx].k;      // every block reads the step index before it takes its ticket below
   const int b = blockIdx.x;
   const float* s = scores + static_cast<size_t>(b) * N;
   for (int i = threadIdx.x; i < N; i += blockDim.x) sm_scores[i] = s[i];
@@ -622,6 +648,17 @@ maskgit_remask_kernel(const float* __restrict__ scores, long long* __restrict__ 
       rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
     }
     if (rank < k) ids[static_cast<size_t>(b) * N + i] = mask_id;
+  }
+  if (step_tab != nullptr) {
+    // last kernel of a MaskGIT step: the block that finishes last advances the step index for the next graph replay
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1) {
+        *ticket = 0;
+        *step_idx += 1;
+      }
+    }
   }
 }
 
@@ -839,10 +876,12 @@ int pm_maskgit_sample_launch(const MaskgitParams& p, cudaStream_t stream) {
   return static_cast<int>(cudaGetLastError());
 }
 
-int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, cudaStream_t stream) {
+int pm_maskgit_remask_launch(const float* scores, long long* ids, int B, int N, int k, long long mask_id, const StepScalars* step_tab,
+                             int* step_idx, int* ticket, cudaStream_t stream) {
   if (scores == nullptr || ids == nullptr || B <= 0 || N <= 0 || k < 0 || N > 12288) return PM_ERR_INVALID;
+  if (step_tab != nullptr && (step_idx == nullptr || ticket == nullptr)) return PM_ERR_INVALID;
   const int threads = N < 1024 ? ((N + 31) / 32) * 32 : 1024;
-  maskgit_remask_kernel<<<B, threads, N * sizeof(float), stream>>>(scores, ids, N, k, mask_id);
+  maskgit_remask_kernel<<<B, threads, N * sizeof(float), stream>>>(scores, ids, N, k, mask_id, step_tab, step_idx, ticket);
   return static_cast<int>(cudaGetLastError());
 }
 

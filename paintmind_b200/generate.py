@@ -217,6 +217,54 @@ class Pipeline(nn.Module):
         self._last_pred_ids, self._last_scores, self._last_logits = pred_ids, scores, logits
         return ids, img
 
+    # ---- one CUDA graph for a whole MaskGIT step (small batches are launch-bound on the host) ----
+    def _step_graph(self, B, context, topk):
+        """Captured sequence ids -> tokens -> transformer -> top-k / gumbel sample -> re-mask, operating in place on static
+        buffers.  The per-step scalars (temperature, re-mask count, Philox key) are read on the device from a table indexed by
+        a device-side step counter that the last kernel advances, so ONE graph serves every step of every generate() call
+        with this (batch, context tensor, topk, weights)."""
+        dev = self.mask_token.device
+        table = self._token_table()
+        eng = self.transformer.engine()
+        eng._ensure_packed()
+        key = (B, topk, table.data_ptr(), table._version, context.data_ptr(), context._version, tuple(context.shape), eng._fp)
+        g = self.__dict__.get("_step_graph_rec")
+        if g is not None and g["key"] == key and g["context"] is context and g["table"] is table:
+            return g
+        N = self.num_tokens
+        st = dict(key=key, context=context, table=table,
+                  ids=torch.full((B, N), self.mask_token_id, dtype=torch.int64, device=dev),
+                  pred_ids=torch.empty(B, N, dtype=torch.int64, device=dev),
+                  scores=torch.empty(B, N, dtype=torch.float32, device=dev),
+                  step_tab=torch.zeros(64 * 24, dtype=torch.uint8, device=dev),     # up to 64 steps of pm_step_scalars
+                  step_idx=torch.zeros(1, dtype=torch.int32, device=dev),
+                  ticket=torch.zeros(1, dtype=torch.int32, device=dev))
+
+        def body():
+            logits = eng.forward_from_ids(st["ids"], table, context)
+            ops.maskgit_sample(logits.view(B * N, -1), topk=topk, temperature=1.0, ids=st["ids"].view(-1),
+                               pred_ids=st["pred_ids"].view(-1), scores=st["scores"].view(-1), mask_id=self.mask_token_id,
+                               step_tab=st["step_tab"], step_idx=st["step_idx"])
+            ops.maskgit_remask_step(st["scores"], st["ids"], self.mask_token_id, st["step_tab"], st["step_idx"], st["ticket"])
+            return logits
+
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):                       # sizes the workspace, fills the context K/V cache
+                body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["logits"] = body()
+        st["graph"] = graph
+        # raw addresses are baked in: pin everything the captured kernels touch (see engine._graphed_forward_from_ids)
+        st["pinned"] = list(eng.ws.bufs.values()) + list(eng._ctx_kv or [])
+        self.__dict__["_step_graph_rec"] = st
+        return st
+
     @torch.no_grad()
     def generate(self, text, timesteps=18, temperature=1.0, topk=5, save_interval=2, decode_every_step=False):
         """MaskGIT iterative decoding (generate.py:183-198) -> list of CPU image tensors (one per kept step).
@@ -237,13 +285,34 @@ class Pipeline(nn.Module):
             side = torch.cuda.Stream(device=dev)
             self.__dict__["_d2h_stream"] = side
         imgs = []
+        use_graph = self.cuda_graph if self.cuda_graph is not None else (B * self.num_tokens <= 16 * 1024)
+        use_graph = use_graph and 1 <= timesteps <= 64 and 1 <= topk <= 32 and context.is_cuda
+        if use_graph:
+            with torch.cuda.device(dev):
+                g = self._step_graph(B, context, topk)
+                # the whole schedule goes to the device once: temperature * (1 - step / T), re-mask counts, one noise key per step
+                temps, ks, offs = [], [], []
+                for step in range(timesteps):
+                    self._advance_rng()
+                    temps.append(temperature * (1 - step / timesteps))
+                    ks.append(max(int(mask_schedule((step + 1) / timesteps) * self.num_tokens), 1))
+                    offs.append(self._rng_calls)
+                tab = ops.step_table(temps, ks, self._rng_seed, offs, dev)
+                g["step_tab"][:tab.numel()].copy_(tab, non_blocking=True)
+                g["step_idx"].zero_()
+                g["ids"].fill_(self.mask_token_id)
         for step in range(timesteps):
             progress = (step + 1) / timesteps
             masked_r = mask_schedule(progress)
             cur_temp = temperature * (1 - step / timesteps)
             keep = (step % save_interval == 0)
-            ids, img = self.sample(ids, mask_ratio=masked_r, text=context, topk=topk, temperature=cur_temp,
-                                   decode=keep or decode_every_step)
+            if use_graph:
+                g["graph"].replay()
+                img = self.vqgan.decode_from_indice(g["pred_ids"]) if (keep or decode_every_step) else None
+                self._last_pred_ids, self._last_scores, self._last_logits = g["pred_ids"], g["scores"], g["logits"]
+            else:
+                ids, img = self.sample(ids, mask_ratio=masked_r, text=context, topk=topk, temperature=cur_temp,
+                                       decode=keep or decode_every_step)
             if keep:
                 host = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
                 ready = torch.cuda.Event()

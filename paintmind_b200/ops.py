@@ -16,11 +16,13 @@ from ._lib import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8  # 
 # Optional per-launch timing (bench.py): when PROFILE is a dict, every op records CUDA events on the
 # launching stream around its kernel launch(es):  PROFILE[key] -> list of (start, end) events.
 PROFILE = None
+PROFILE_ONLY = None   # optional set of op names (key[0]): only these are bracketed by events (bench.py times the dominant kernel
+                      # inside its timed region this way and the full per-kernel table in a separate, untimed pass)
 LAUNCHES = 0          # kernels launched through this module (bench.py's gpu_launches)
 
 
 def _prof_begin():
-    if PROFILE is None:
+    if PROFILE is None or PROFILE_ONLY is not None:       # selective mode: only ops that call _prof_selected record events
         return None
     ev = torch.cuda.Event(enable_timing=True)
     ev.record()
@@ -30,6 +32,22 @@ def _prof_begin():
 def _prof_end(start, key, nkernels=1):
     global LAUNCHES
     LAUNCHES += nkernels
+    if start is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        PROFILE.setdefault(key, []).append((start, ev))
+
+
+def _prof_selected(name):
+    """(start event or None) for an op that supports selective profiling: records only when `name` is selected."""
+    if PROFILE is None or PROFILE_ONLY is None or name not in PROFILE_ONLY:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_selected_end(start, key):
     if start is not None:
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
@@ -131,7 +149,9 @@ def attention(q, k, v, o, heads, scale):
     args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
     args.scale = float(scale)
     t0 = _prof_begin()
+    ts = _prof_selected("attention")
     _lib.check(_lib.load().pm_attn_fwd(C.byref(args), _stream()), "pm_attn_fwd")
+    _prof_selected_end(ts, ("attention", args.B, args.H, args.Nq, args.Nk))
     _prof_end(t0, ("attention", args.B, args.H, args.Nq, args.Nk))
     return o
 
@@ -225,10 +245,13 @@ def layernorm(x, *, gamma=None, beta=None, y=None, stats=None, eps=1e-5):
     _prof_end(t0, ("layernorm" if y is not None else "ln_stats", M, D))
 
 
-def maskgit_sample(logits2d, *, topk, temperature, ids=None, pred_ids, scores, mask_id, noise=None, seed=0, offset=0):
-    """Fused top-k + gumbel arg-max + mask fill + confidence (generate.py:163-173) over fp32 logits [M, V]."""
+def maskgit_sample(logits2d, *, topk, temperature, ids=None, pred_ids, scores, mask_id, noise=None, seed=0, offset=0,
+                   step_tab=None, step_idx=None):
+    """Fused top-k + gumbel arg-max + mask fill + confidence (generate.py:163-173) over fp32 logits [M, V].
+    `step_tab` / `step_idx` (device tensors, see step_table): temperature / seed / offset are read on the device."""
     _require_cuda(logits2d, pred_ids, scores)
     a = _lib.MaskgitSampleArgs()
+    a.step_tab, a.step_idx = _ptr(step_tab), _ptr(step_idx)
     a.logits, a.noise, a.ids, a.pred_ids, a.scores = _ptr(logits2d), _ptr(noise), _ptr(ids), _ptr(pred_ids), _ptr(scores)
     a.ld = logits2d.stride(0)
     a.ld_noise = noise.stride(0) if noise is not None else 0
@@ -246,6 +269,24 @@ def maskgit_remask(scores2d, ids2d, k, mask_id):
     t0 = _prof_begin()
     _lib.check(_lib.load().pm_maskgit_remask(_ptr(scores2d), _ptr(ids2d), B, N, int(k), int(mask_id), _stream()),
                "pm_maskgit_remask")
+    _prof_end(t0, ("maskgit_remask", B, N))
+
+
+def step_table(temperatures, ks, seed, offsets, device):
+    """Device table of pm_step_scalars (one 24-byte entry per MaskGIT step) as a uint8 tensor."""
+    import numpy as np
+    rec = np.zeros(len(ks), dtype=np.dtype([("temperature", "<f4"), ("k", "<i4"), ("seed", "<u8"), ("offset", "<u8")]))
+    rec["temperature"], rec["k"], rec["seed"], rec["offset"] = temperatures, ks, np.uint64(int(seed) & (2 ** 64 - 1)), offsets
+    return torch.from_numpy(rec.view(np.uint8).copy()).to(device)
+
+
+def maskgit_remask_step(scores2d, ids2d, mask_id, step_tab, step_idx, ticket):
+    """maskgit_remask with k read from step_tab[*step_idx]; advances *step_idx (last kernel of a graph-captured step)."""
+    _require_cuda(scores2d, ids2d, step_tab, step_idx, ticket)
+    B, N = scores2d.shape
+    t0 = _prof_begin()
+    _lib.check(_lib.load().pm_maskgit_remask_step(_ptr(scores2d), _ptr(ids2d), B, N, int(mask_id), _ptr(step_tab), _ptr(step_idx),
+                                                  _ptr(ticket), _stream()), "pm_maskgit_remask_step")
     _prof_end(t0, ("maskgit_remask", B, N))
 
 

@@ -44,7 +44,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.AttnArgs) == 4 * 8 + 8 * 8 + 5 * 4 + 4 + 4 * 8          # + lse, lse_ld, o32, ldo32
     assert ctypes.sizeof(_lib.AttnBwdArgs) == 10 * 8 + 16 * 8 + 5 * 4 + 4 + 4 + 4 + 2 * 8   # 10 ptrs, 16 i64, 5 i32, f32, i32, pad, i64, ptr
     assert ctypes.sizeof(_lib.VqArgs) == 10 * 8 + 8 + 4 * 4
-    assert ctypes.sizeof(_lib.MaskgitSampleArgs) == 5 * 8 + 3 * 8 + 2 * 8 + 3 * 4 + 4
+    assert ctypes.sizeof(_lib.MaskgitSampleArgs) == 5 * 8 + 3 * 8 + 2 * 8 + 3 * 4 + 4 + 2 * 8      # + step_tab, step_idx
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions():

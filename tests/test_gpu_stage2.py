@@ -245,8 +245,9 @@ def test_pipeline_generate_lazy_decode_equals_per_step_decode(cuda_device, full_
 
 
 def test_pipeline_generate_cuda_graph_equals_eager(cuda_device, full_pipeline):
-    """Small batches replay the transformer forward from a CUDA graph (Pipeline.cuda_graph): same images, bit for bit, and the
-    graph follows a changed text context."""
+    """Small batches replay a whole MaskGIT step (ids -> tokens -> transformer -> sample -> re-mask) from ONE CUDA graph whose
+    per-step scalars (temperature, re-mask count, noise key) live in a device table (Pipeline.cuda_graph): same images as the
+    eager loop, bit for bit, at every kept step, and the graph follows a changed text context."""
     pipe = full_pipeline
     g = torch.Generator().manual_seed(5)
     outs = {}
@@ -256,11 +257,13 @@ def test_pipeline_generate_cuda_graph_equals_eager(cuda_device, full_pipeline):
         for text_seed in (1, 2):
             text = torch.randn(2, 77, 1024, generator=torch.Generator().manual_seed(text_seed)).to(cuda_device)
             torch.manual_seed(99)              # the sampling noise is keyed on the torch generator state
-            res.append(pipe.generate(text, timesteps=3, temperature=1.0, topk=5, save_interval=3)[0])
+            res.extend(pipe.generate(text, timesteps=5, temperature=1.0, topk=5, save_interval=2))
         outs[mode] = res
     pipe.cuda_graph = None
+    assert len(outs[True]) == 6                                   # 2 prompts x steps 0, 2, 4
     assert all(torch.equal(a, b) for a, b in zip(outs[False], outs[True]))
-    assert not torch.equal(outs[True][0], outs[True][1])
+    assert not torch.equal(outs[True][0], outs[True][3])          # another prompt, another image
+    assert not torch.equal(outs[True][0], outs[True][1])          # another step, another image
 
 
 def _run_sample(logits2d, u2d, topk, temp, V):
