@@ -66,6 +66,16 @@ class Pipeline(nn.Module):
         self._table = None
         self._table_fp = None
 
+    def invalidate(self):
+        """Drop every cache keyed on parameter versions (packed weights, token table, CUDA graphs): call after writes that
+        bypass autograd's version counter (`p.data.copy_(...)`, EMA, weight surgery)."""
+        self._table_fp = None
+        self.__dict__.pop("_step_graph_rec", None)
+        self.vqgan.invalidate()
+        eng = self.transformer.__dict__.get("_engine")
+        if eng is not None:
+            eng.invalidate()
+
     def _advance_rng(self):
         """Philox key / counter of the next sampling call, drawn from torch's default generator: (torch.initial_seed(), one
         31-bit draw).  Results are therefore a function of the torch RNG state — `torch.manual_seed(s)` before generate() /

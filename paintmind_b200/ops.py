@@ -328,10 +328,10 @@ _WORK = {}
 
 
 def _workspace(name, nfloats, device):
-    """fp32 scratch reused across calls (split-K partial tiles, column-sum partials).  One buffer per (purpose, device): calls
-    are ordered by the stream they are enqueued on, so this is safe for the single-stream use of train.py; a host that
-    drives several streams concurrently passes its own workspaces to the C-ABI (every entry point takes them as arguments)."""
-    key = (name, str(device))
+    """fp32 scratch reused across calls (split-K partial tiles, column-sum partials).  One buffer per (purpose, device, STREAM):
+    calls on one stream are ordered, and two streams never share a buffer, so concurrent use from several streams is safe
+    (round 1 keyed on (purpose, device) only).  The C-ABI itself takes every workspace as an argument."""
+    key = (name, str(device), torch.cuda.current_stream(device).cuda_stream)
     t = _WORK.get(key)
     if t is None or t.numel() < nfloats:
         t = torch.empty(max(int(nfloats), 1), device=device, dtype=torch.float32)

@@ -7,7 +7,9 @@ The decoder of vit-s-vqgan (stage1/layers.py:145-152 + vqmodel.py:27-30) is eval
   ours     : the CUDA path's layout: bf16 operands, fp32 accumulation, LayerNorm folded into the next GEMM
              (raw bf16 x as the A operand), bf16 q|k|v, P, attention output and SwiGLU hidden, and a BF16 RESIDUAL STREAM (one
              rounding of x after every residual update);
-  ours+f32x: the same with the residual stream kept in fp32 (what a hi+lo / fp32 residual would buy).
+  ours+f32x: the same with the residual stream kept in fp32 (what a hi+lo / fp32 residual would buy);
+  ours+f16x: the same with the residual stream in FP16 (same bytes as bf16, 11 instead of 8 significant bits; the GEMM A operand is
+             then the fp16 x itself).
 Prints max / mean abs error of the clamped reconstruction against fp32, on all pixels of both images.
 """
 import sys
@@ -35,7 +37,7 @@ def bf(t):
 def decoder(z, mode):
     r = (lambda t: t) if mode == "fp32" else bf                         # operand rounding
     out_r = bf if mode == "autocast" else (lambda t: t)                 # autocast: Linear returns bf16
-    x_r = bf if mode == "ours" else (lambda t: t)                       # residual-stream rounding
+    x_r = bf if mode == "ours" else (lambda t: t.to(torch.float16).float()) if mode == "ours+f16x" else (lambda t: t)   # residual-stream rounding
     dcfg = cfg["dec"]
     H = dcfg["num_head"]
 
@@ -54,7 +56,8 @@ def decoder(z, mode):
                 mu = x.mean(-1, keepdim=True)
                 rstd = (x.var(-1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
                 wf = bf(w * gam[None, :])
-                y = rstd * (F.linear(bf(x), wf) - mu * wf.sum(1)[None, None, :]) + (F.linear(bet[None], w)[0] + (b if b is not None else 0))
+                xa = x if mode == "ours+f16x" else bf(x)          # fp16 residual stream: the A operand is x itself (fp16 x bf16 products are exact in fp32)
+                y = rstd * (F.linear(xa, wf) - mu * wf.sum(1)[None, None, :]) + (F.linear(bet[None], w)[0] + (b if b is not None else 0))
                 return y
             return lin(F.layer_norm(x, (x.shape[-1],), gam, bet, 1e-5), w, b)
 
@@ -83,7 +86,8 @@ def decoder(z, mode):
         rstd = (x.var(-1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
         w = sd["decoder.proj.weight"]
         wf = bf(w * gam[None, :])
-        y = rstd * (F.linear(bf(x), wf) - mu * wf.sum(1)[None, None, :]) + (F.linear(bet[None], w)[0] + sd["decoder.proj.bias"])
+        xa = x if mode == "ours+f16x" else bf(x)
+        y = rstd * (F.linear(xa, wf) - mu * wf.sum(1)[None, None, :]) + (F.linear(bet[None], w)[0] + sd["decoder.proj.bias"])
     else:
         y = F.linear(r(F.layer_norm(x, (x.shape[-1],), sd["decoder.norm.weight"], sd["decoder.norm.bias"], 1e-5)), r(sd["decoder.proj.weight"]),
                      sd["decoder.proj.bias"]).float()
@@ -95,6 +99,6 @@ with torch.no_grad():
     ref = decoder(zq, "fp32")
     s = int(g["rec_stride"])
     print(f"fp32 emulation vs the reference fixture: max {float((ref[:, :, ::s, ::s] - torch.from_numpy(g['rec_sub'])).abs().max()):.2e}")
-    for mode in ("autocast", "ours", "ours+f32x"):
+    for mode in ("autocast", "ours", "ours+f32x", "ours+f16x"):
         err = (decoder(zq, mode) - ref).abs()
         print(f"{mode:10s} max {float(err.max()):.4f}  mean {float(err.mean()):.5f}  p99.9 {float(err.flatten().kthvalue(int(0.999 * err.numel())).values):.4f}")
