@@ -114,6 +114,10 @@ typedef struct pm_attn_args {
   int64_t lse_ld;                  /* row pitch of lse (0 = Nq); pm_attn_bwd wants Nq rounded up to a multiple of 128 */
   float* o32;                      /* optional out: fp32 copy of O, [B, Nq, ldo32] dense over the batch (training forward: */
   int64_t ldo32;                   /* keeps delta = rowsum(dO * O) of the backward free of O's bf16 rounding); else NULL   */
+  int32_t q_prescaled;             /* != 0: Q already carries scale * log2(e) (folded into the to_q weight rows by the caller):
+                                      `scale` is ignored, softmax(Q K^T in base 2) is computed by the bias-MMA kernel
+                                      (pm_attn3.cu: the row maximum is subtracted by the tensor core) */
+  int32_t reserved;
 } pm_attn_args;
 
 int pm_attn_fwd(const pm_attn_args* args, void* stream);

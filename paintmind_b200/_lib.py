@@ -37,6 +37,7 @@ class AttnArgs(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("head_dim", C.c_int32),
         ("scale", C.c_float),
         ("lse", C.c_void_p), ("lse_ld", C.c_int64), ("o32", C.c_void_p), ("ldo32", C.c_int64),
+        ("q_prescaled", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

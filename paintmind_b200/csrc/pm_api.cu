@@ -75,7 +75,8 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
   p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ldo;
   p.bsq = a->bsq; p.bsk = a->bsk; p.bsv = a->bsv; p.bso = a->bso;
   p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.head_dim = a->head_dim;
-  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.prescaled = a->q_prescaled != 0 ? 1 : 0;
+  p.scale_log2 = p.prescaled ? 1.0f : a->scale * 1.4426950408889634f;
   p.lse = a->lse;
   p.lse_ld = a->lse_ld > 0 ? a->lse_ld : a->Nq;
   p.o32 = a->o32;
@@ -86,6 +87,18 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
   if (impl == 0) {
     const char* env = getenv("PM_ATTN_IMPL");
     impl = (env != nullptr && env[0] == '2') ? 2 : 1;
+  }
+  // pre-scaled queries: the bias-MMA kernel (PM_ATTN_IMPL set = A/B against the older kernels, which take scale_log2 = 1)
+  if (p.prescaled && getenv("PM_ATTN_IMPL") == nullptr && pm_attn3_supported(p)) {
+    // default: the 16-softmax-warp kernel (pm_attn4.cu; sustained, i.e. power-capped: 0.721 ms at B = 256, H = 8, N = 1024 against
+    // 0.734-0.741 for the 8-warp pm_attn3.cu and 0.759 for pm_attn.cu — profiles/r02_attention.md).  PM_ATTN_PRE=3 picks pm_attn3.cu.
+    static int pre_impl = 0;
+    if (pre_impl == 0) {
+      const char* env = getenv("PM_ATTN_PRE");
+      pre_impl = (env != nullptr && env[0] == '3') ? 3 : 4;
+    }
+    if (pre_impl == 4) return pm_attn4_launch(p, static_cast<cudaStream_t>(stream));
+    return pm_attn3_launch(p, static_cast<cudaStream_t>(stream));
   }
   if (impl == 2) return pm_attn2_launch(p, static_cast<cudaStream_t>(stream));
   return pm_attn_launch(p, static_cast<cudaStream_t>(stream));

@@ -44,6 +44,7 @@ struct AttnParams {
   int64_t lse_ld;                  // row pitch of lse per (batch, head): >= Nq (pm_attn_bwd wants it rounded up to 128)
   float* o32;                      // optional [B, Nq, ldo32] fp32 copy of O (training forward; feeds delta of the backward)
   int64_t ldo32;
+  int prescaled;                   // Q carries scale * log2(e): scale_log2 is 1 (pm_attn3.cu)
 };
 
 struct AttnBwdParams {
@@ -145,6 +146,10 @@ int pm_ce_label_smooth_launch(const float* logits, int64_t ld, int M, int V, con
                               float eps, float* row_loss, float* loss_out, double* sums_out, cudaStream_t stream);
 int pm_attn_launch(const AttnParams& p, cudaStream_t stream);
 int pm_attn2_launch(const AttnParams& p, cudaStream_t stream);
+int pm_attn3_launch(const AttnParams& p, cudaStream_t stream);
+bool pm_attn3_supported(const AttnParams& p);
+int pm_attn4_launch(const AttnParams& p, cudaStream_t stream);
+bool pm_attn4_supported(const AttnParams& p);
 int pm_attn_bwd_launch(const AttnBwdParams& p, cudaStream_t stream);
 int pm_attn_delta_launch(const void* o, int o_is_f32, int64_t ldo, int64_t bso, const void* dO, int64_t lddo, int64_t bsdo, int B, int H,
                          int N, const float* lse, float scale, float* nds, float* nlse, int64_t delta_ld, cudaStream_t stream);

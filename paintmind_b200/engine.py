@@ -25,6 +25,7 @@ from . import ops
 from .ops import PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8
 
 LN_EPS = 1e-5
+LOG2E = 1.4426950408889634
 
 
 def _ceil_to(v, m):
@@ -93,6 +94,12 @@ class _Block:
         a1 = layer.attn1
         wqkv = torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], dim=0).detach()
         self.w_qkv, self.cs_qkv, self.b_qkv = fold_layernorm(wqkv, None, layer.norm1.weight.detach(), layer.norm1.bias.detach())
+        # inference copy with scale * log2(e) folded into the to_q rows (before the bf16 rounding): the attention kernel for
+        # pre-scaled queries (pm_attn3.cu) then exponentiates Q K^T as it leaves the tensor core.  The training engine keeps
+        # the unscaled operands above (its backward kernels take the scale as a parameter).
+        wq_ps = torch.cat([a1.to_q.weight.detach().float() * (float(a1.scale) * LOG2E), a1.to_k.weight.detach().float(),
+                           a1.to_v.weight.detach().float()], dim=0)
+        self.w_qkv_ps, self.cs_qkv_ps, self.b_qkv_ps = fold_layernorm(wq_ps, None, layer.norm1.weight.detach(), layer.norm1.bias.detach())
         self.w_o = a1.to_out[0].weight.detach().to(torch.bfloat16).contiguous()
         self.b_o = a1.to_out[0].bias.detach().float().contiguous()
         self.inner = a1.to_q.weight.shape[0]
@@ -101,7 +108,8 @@ class _Block:
         self.cross = cross
         if cross:
             a2 = layer.attn2
-            self.w_q2, self.cs_q2, self.b_q2 = fold_layernorm(a2.to_q.weight.detach(), None, layer.norm2.weight.detach(), layer.norm2.bias.detach())
+            self.w_q2, self.cs_q2, self.b_q2 = fold_layernorm(a2.to_q.weight.detach().float() * (float(a2.scale) * LOG2E), None,
+                                                              layer.norm2.weight.detach(), layer.norm2.bias.detach())      # pre-scaled q
             self.w_kv2 = torch.cat([a2.to_k.weight, a2.to_v.weight], dim=0).detach().to(torch.bfloat16).contiguous()
             # context=None -> attn2 is a second self-attention over LN2(x) (attention.py:47): fold LN2 into k/v too
             wkv = torch.cat([a2.to_k.weight, a2.to_v.weight], dim=0).detach()
@@ -183,9 +191,9 @@ def run_blocks(blocks, x, st, B, N, ws, context_kv=None, ctx_len=0):
         qkv = ws.get("qkv", (M, 3 * inner), torch.bfloat16, dev)
         ao = ws.get("ao", (M, inner), torch.bfloat16, dev)
         # x = attn1(norm1(x)) + x
-        ops.gemm(x, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, **st.consume())
+        ops.gemm(x, blk.w_qkv_ps, qkv, bias=blk.b_qkv_ps, colsum=blk.cs_qkv_ps, **st.consume())
         q3 = qkv.view(B, N, 3 * inner)
-        ops.attention(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), blk.heads, blk.scale)
+        ops.attention(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), blk.heads, blk.scale, prescaled=True)
         ops.gemm(ao, blk.w_o, x, bias=blk.b_o, res=x, stats_out=st.produce())
         if blk.cross:
             # x = attn2(norm2(x), context) + x
@@ -198,7 +206,7 @@ def run_blocks(blocks, x, st, B, N, ws, context_kv=None, ctx_len=0):
                 kv = ws.get("kv2", (M, 2 * inner), torch.bfloat16, dev)
                 ops.gemm(x, blk.w_kv2_self, kv, bias=blk.b_kv2_self, colsum=blk.cs_kv2_self, **st.consume())
                 kv3 = kv.view(B, N, 2 * inner)
-            ops.attention(q2.view(B, N, inner), kv3[..., :inner], kv3[..., inner:], ao.view(B, N, inner), blk.heads, blk.scale2)
+            ops.attention(q2.view(B, N, inner), kv3[..., :inner], kv3[..., inner:], ao.view(B, N, inner), blk.heads, blk.scale2, prescaled=True)
             ops.gemm(ao, blk.w_o2, x, bias=blk.b_o2, res=x, stats_out=st.produce())
         # x = ffnet(norm(x)) + x
         h = ws.get("h", (M, blk.hp), torch.bfloat16, dev)

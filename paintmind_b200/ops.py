@@ -139,8 +139,9 @@ def gemm(a, w, out, *, bias=None, colsum=None, stats=None, pos=None, res=None, o
     return out
 
 
-def attention(q, k, v, o, heads, scale):
-    """q,o: [B, Nq, >=heads*64] views; k,v: [B, Nk, ...] views (bf16, last stride 1)."""
+def attention(q, k, v, o, heads, scale, prescaled=False):
+    """q,o: [B, Nq, >=heads*64] views; k,v: [B, Nk, ...] views (bf16, last stride 1).  prescaled: q already carries
+    scale * log2(e) (engine.py folds it into the to_q weight rows); `scale` is then ignored."""
     _require_cuda(q, k, v, o)
     args = _lib.AttnArgs()
     args.q, args.k, args.v, args.o = _ptr(q), _ptr(k), _ptr(v), _ptr(o)
@@ -148,6 +149,7 @@ def attention(q, k, v, o, heads, scale):
     args.bsq, args.bsk, args.bsv, args.bso = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
     args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
     args.scale = float(scale)
+    args.q_prescaled = int(bool(prescaled))
     t0 = _prof_begin()
     ts = _prof_selected("attention")
     _lib.check(_lib.load().pm_attn_fwd(C.byref(args), _stream()), "pm_attn_fwd")

@@ -137,6 +137,7 @@ class Stage1TrainEngine:
         ops.gemm(x, e.w_prev, z, bias=e.b_prev, out_mode=PM_OUT_F32, bn=32)
         r = m.quantize.quantize_2d(z, want_split=True)
         sv["z"], sv["idx"], sv["zs"] = z, r["idx"], r["zq_split"]
+        self.last_indices = r["idx"].view(B, N)      # code indices of the latest training forward (usage monitoring, tests)
         loss = (r["sse"] * ((1.0 + m.quantize.beta) / (M * m.quantize.e_dim))).to(torch.float32).reshape(())
         # decoder
         Dd = dec.dim

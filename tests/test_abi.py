@@ -41,7 +41,7 @@ def test_struct_layouts_match_header_sizes():
     """ctypes mirrors of the argument structs: natural alignment, pointer/int64 fields first then int32."""
     from paintmind_b200 import _lib
     assert ctypes.sizeof(_lib.GemmArgs) == 8 * 8 + 5 * 8 + 12 * 4 + 4 + 4 + 8 + 8 + 8 + 8  # 8 ptrs, 5 i64, 12 i32, f32, pad, ptr, i32+pad, ptr, i32+pad
-    assert ctypes.sizeof(_lib.AttnArgs) == 4 * 8 + 8 * 8 + 5 * 4 + 4 + 4 * 8          # + lse, lse_ld, o32, ldo32
+    assert ctypes.sizeof(_lib.AttnArgs) == 4 * 8 + 8 * 8 + 5 * 4 + 4 + 4 * 8 + 2 * 4  # + lse, lse_ld, o32, ldo32, q_prescaled, reserved
     assert ctypes.sizeof(_lib.AttnBwdArgs) == 10 * 8 + 16 * 8 + 5 * 4 + 4 + 4 + 4 + 2 * 8   # 10 ptrs, 16 i64, 5 i32, f32, i32, pad, i64, ptr
     assert ctypes.sizeof(_lib.VqArgs) == 10 * 8 + 8 + 4 * 4
     assert ctypes.sizeof(_lib.MaskgitSampleArgs) == 5 * 8 + 3 * 8 + 2 * 8 + 3 * 4 + 4 + 2 * 8      # + step_tab, step_idx
