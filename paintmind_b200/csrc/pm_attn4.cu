@@ -90,10 +90,21 @@ __device__ __forceinline__ void a4_exps(const uint32_t (&s)[2][32], float delta,
       float2 a = make_float2(__uint_as_float(s[ch][e]), __uint_as_float(s[ch][e + 1]));
       if (SHIFT) a = __fadd2_rn(a, dd2);
       const bool poly = ((e >> 1) & 3) < EMU;
+#if defined(PM_A4_EXPERIMENT) && PM_A4_EXPERIMENT >= 1
+      // energy experiments (wrong results): 1 = no exponentials, 2 = no exponentials and no row sums, 3 = also no bf16 packing
+      const float2 ex = a;
+#else
       const float2 ex = poly ? a4_exp2_poly2(a) : make_float2(a4_ex2(a.x), a4_ex2(a.y));
+#endif
+#if !defined(PM_A4_EXPERIMENT) || PM_A4_EXPERIMENT < 2
       if ((e >> 1) & 1) lb = __fadd2_rn(lb, ex);
       else la = __fadd2_rn(la, ex);
+#endif
+#if defined(PM_A4_EXPERIMENT) && PM_A4_EXPERIMENT >= 3
+      pk[ch][e >> 1] = __float_as_uint(ex.x) ^ __float_as_uint(ex.y);
+#else
       pk[ch][e >> 1] = pack_bf16x2(ex.x, ex.y);
+#endif
     }
   }
 }

@@ -1,7 +1,6 @@
-"""The pre-scaled-query attention kernel (pm_attn3.cu: row maximum subtracted by the tensor core, no per-tile maximum
-after the first key tile) against fp32 softmax attention (reference modules/attention.py:51-58), including the inputs its
-short-cuts must survive: ragged key / query counts (mask through the bias operand), logits that grow by 2^30..2^90 between
-key tiles (re-centring path) and by more than fp32's exponent range (overflow -> exact re-run of the work item)."""
+"""The pre-scaled-query attention kernels (pm_attn4.cu, 16 softmax warps, the default; pm_attn3.cu, 8 warps: row maximum
+subtracted by the tensor core, no per-tile maximum after the first key tile) against fp32 softmax attention (reference modules/attention.py:51-58), including the inputs its
+short-cuts must survive: ragged key / query counts (mask through the bias operand), logits tens of binades above the first key tile's maximum (stale-maximum path) and by more than fp32's exponent range (overflow -> exact re-run of the work item)."""
 import math
 
 import pytest
@@ -63,8 +62,8 @@ def test_prescaled_attention_views_of_a_packed_qkv_buffer(cuda_device):
 
 @pytest.mark.parametrize("gain", [2.0, 3.0])
 def test_prescaled_attention_large_logits_recentre(cuda_device, gain):
-    """Base-2 logits with a standard deviation of 46-100: later key tiles exceed the first tile's maximum by tens of binades,
-    the running sum passes 2^30 and the accumulators are re-centred (m moved, O rescaled) — results must still match."""
+    """Base-2 logits with a standard deviation of 46-100: later key tiles exceed the first tile's maximum by tens of binades
+    (P far above 1, rows beyond 2^100 are re-run exactly) — results must still match."""
     torch.manual_seed(11)
     B, N, H = 3, 640, 2
     q = (torch.randn(B, N, 128, device=cuda_device) * gain * LOG2E).bfloat16()
@@ -106,3 +105,26 @@ def test_prescaled_matches_unscaled_kernel(cuda_device):
     ops.attention(q.bfloat16(), k, v, o1, H, 0.125)
     o3 = _run((q * (0.125 * LOG2E)).bfloat16(), k, v, H)
     assert (o1.float() - o3).abs().max().item() < 0.02
+
+
+def test_eight_warp_variant_in_a_subprocess(cuda_device):
+    """PM_ATTN_PRE=3 selects pm_attn3.cu (8 softmax warps; the library reads the variable once per process): same checks, one
+    child process — self-attention, ragged 77-key cross-attention, several items per CTA, and the overflow re-run."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    child = r"""
+import sys, math, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import test_gpu_attention3 as T
+dev = torch.device("cuda:0")
+for (B, Nq, Nk, heads) in [(3, 1024, 1024, 8), (2, 1024, 77, 16), (160, 256, 256, 1), (3, 200, 200, 2)]:
+    T.test_prescaled_attention_vs_fp32_softmax(dev, B, Nq, Nk, heads)
+T.test_prescaled_attention_large_logits_recentre(dev, 2.0)
+T.test_prescaled_attention_overflow_falls_back_to_exact_pass(dev)
+print("CHILD OK")
+""" % (str(root), str(root / "tests"))
+    r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, PM_ATTN_PRE="3"), capture_output=True, text=True, timeout=300)
+    assert "CHILD OK" in r.stdout, r.stdout[-800:] + r.stderr[-1500:]
