@@ -89,7 +89,7 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
     impl = (env != nullptr && env[0] == '2') ? 2 : 1;
   }
   // pre-scaled queries: the bias-MMA kernel (PM_ATTN_IMPL set = A/B against the older kernels, which take scale_log2 = 1)
-  if (p.prescaled && getenv("PM_ATTN_IMPL") == nullptr && pm_attn3_supported(p)) {
+  if (p.prescaled && getenv("PM_ATTN_IMPL") == nullptr && pm_attn4_supported(p)) {
     // default: the 16-softmax-warp kernel (pm_attn4.cu; sustained, i.e. power-capped: 0.721 ms at B = 256, H = 8, N = 1024 against
     // 0.734-0.741 for the 8-warp pm_attn3.cu and 0.759 for pm_attn.cu — profiles/r02_attention.md).  PM_ATTN_PRE=3 picks pm_attn3.cu.
     static int pre_impl = 0;
@@ -97,7 +97,7 @@ int pm_attn_fwd(const pm_attn_args* a, void* stream) {
       const char* env = getenv("PM_ATTN_PRE");
       pre_impl = (env != nullptr && env[0] == '3') ? 3 : 4;
     }
-    if (pre_impl == 4) return pm_attn4_launch(p, static_cast<cudaStream_t>(stream));
+    if (pre_impl == 4 || p.lse != nullptr || p.o32 != nullptr) return pm_attn4_launch(p, static_cast<cudaStream_t>(stream));
     return pm_attn3_launch(p, static_cast<cudaStream_t>(stream));
   }
   if (impl == 2) return pm_attn2_launch(p, static_cast<cudaStream_t>(stream));

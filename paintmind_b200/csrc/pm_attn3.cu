@@ -442,6 +442,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           tmem_ld_x32(tS + 96, s[3]);
           tmem_ld_wait();
           A3_DBG_LAP(1)
+          const bool last = j == n_kv - 1;
           const float m_tile = m_baked;              // the offset this tile was issued with
           bool shifted;
           bool waited_pv = false;
@@ -483,10 +484,11 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             shifted = false;
           }
           A3_DBG_LAP(24)
-          // ---- publish the offset the NEXT score tile of this Q tile is issued with (fast pass only; the next item's first tile
-          //      simply arrives with this item's offset, which its maximum pass adds back), then hand S_t back ----
-          if (!exact && j == 0) {
-            const float m_next = (fabsf(m_used) < 3.0e38f) ? m_used : 0.0f;      // never publish inf / NaN (inf / NaN inputs)
+          // ---- publish the offset the NEXT score tile of this Q tile is issued with (fast pass only), then hand S_t back ----
+          // every item's FIRST tile is issued with offset 0 (written back on the item's last tile), so that a row's result does
+          // not depend on what the CTA processed before: batch-invariant bits
+          if (!exact && (j == 0 || last)) {
+            const float m_next = (!last && fabsf(m_used) < 3.0e38f) ? m_used : 0.0f;      // never publish inf / NaN
             if (m_next != m_baked) {
               const uint32_t w = 0x3F800000u | (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(-m_next))));
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_row), "r"(w) : "memory");
@@ -498,7 +500,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           A3_DBG_LAP(25)
           tc_fence_before();
           A3_DBG_LAP(26)
-          if (j == 0 || exact) {
+          if (j == 0 || last || exact) {
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_s_free);                            // release: orders the lanes' A_t writes
           } else if (lane == 0) {

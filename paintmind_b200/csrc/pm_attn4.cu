@@ -109,7 +109,8 @@ __device__ __forceinline__ void a4_exps(const uint32_t (&s)[2][32], float delta,
   }
 }
 
-template <int EMU>
+// TRAIN : also emit the row log-sum-exp (base 2, of the pre-scaled logits) and an fp32 copy of the output (training forward)
+template <int EMU, bool TRAIN>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
@@ -378,7 +379,9 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             if (j == 0) {
               m_used = a4_bf16_round(mt);
               if (!exact) {
-                const float m_next = (fabsf(m_used) < 3.0e38f) ? m_used : 0.0f;      // never publish inf / NaN
+                // offset for the item's remaining tiles; a single-tile item leaves A_t at 0 (every item's FIRST tile is issued
+                // with offset 0, so that a row's result does not depend on what the CTA processed before: batch-invariant bits)
+                const float m_next = (n_kv > 1 && fabsf(m_used) < 3.0e38f) ? m_used : 0.0f;      // never publish inf / NaN
                 if (m_next != m_baked) {
                   if (kh == 0) {
                     const uint32_t w = 0x3F800000u | (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(-m_next))));
@@ -424,8 +427,21 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             tmem_ld_x32(tS_own + 32, s[1]);
             tmem_ld_wait();
             tc_fence_before();
-            // nothing but completed tcgen05.ld reads to publish (ordered by the tcgen05 fence)
-            if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(b_s_free) : "memory");
+            if (j == n_kv - 1) {
+              // last tile of the item: the next item's first tile must be issued with offset 0 (see above)
+              if (m_baked != 0.0f) {
+                if (kh == 0) {
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_row), "r"(0x3F800000u) : "memory");
+                  fence_proxy_async_smem();
+                }
+                m_baked = 0.0f;
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive_a(b_s_free);                          // release: orders the A_t writes
+            } else if (lane == 0) {
+              // nothing but completed tcgen05.ld reads to publish (ordered by the tcgen05 fence)
+              asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(b_s_free) : "memory");
+            }
             ok_pv = mbar_try_wait_a(b_pv_done, (g - 1) & 1);          // poll issued now, consumed after the exponentials
             a4_exps<false, EMU>(s, 0.0f, la, lb, pk);
           }
@@ -456,10 +472,26 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const float inv_l = 1.0f / l_sum;
         mbar_wait_a(b_pv_done, (g - 1) & 1);
         tc_fence_after();
+        const int qrow = it.qb * 2 * A4_BM + t * A4_BM + row_in_tile;
+        if (TRAIN && p.lse != nullptr && kh == 0) {
+          // training forward: base-2 log-sum-exp of the score row, consumed by pm_attn_bwd (a flagged item's value is
+          // overwritten by the exact pass: same thread, program order)
+          if (qrow < p.Nq) p.lse[(static_cast<size_t>(it.b) * p.H + it.h) * p.lse_ld + qrow] = m_used + log2f(l_sum);
+        }
         uint32_t r0[32];
         tmem_ld_x32(tO + kh * 32, r0);
         tmem_ld_wait();
         // (O_t is free again: the next item's first P V is only issued after BOTH halves' next p_full arrivals)
+        if (TRAIN && p.o32 != nullptr) {
+          // training forward: an fp32 copy of the output rows (keeps delta = rowsum(dO * O) free of O's bf16 rounding)
+          if (qrow < p.Nq) {
+            float4* dst = reinterpret_cast<float4*>(p.o32 + (static_cast<size_t>(it.b) * p.Nq + qrow) * p.ldo32 + it.h * A4_D + kh * 32);
+#pragma unroll
+            for (int jv = 0; jv < 8; ++jv)
+              __stcs(dst + jv, make_float4(__uint_as_float(r0[jv * 4 + 0]) * inv_l, __uint_as_float(r0[jv * 4 + 1]) * inv_l,
+                                           __uint_as_float(r0[jv * 4 + 2]) * inv_l, __uint_as_float(r0[jv * 4 + 3]) * inv_l));
+          }
+        }
 #pragma unroll
         for (int jv = 0; jv < 4; ++jv) {
           uint4 o;
@@ -501,13 +533,12 @@ struct Attn4Variant {
 };
 // The first entry is the default; PM_ATTN4_VARIANT="emu" picks another one (tuning aid, same function).
 static const Attn4Variant kAttn4Variants[] = {
-    {1, attn4_kernel<1>},
-    {0, attn4_kernel<0>},
-    {2, attn4_kernel<2>},
+    {1, attn4_kernel<1, false>},
+    {0, attn4_kernel<0, false>},
+    {2, attn4_kernel<2, false>},
 };
 
 bool pm_attn4_supported(const AttnParams& p) {
-  if (p.lse != nullptr || p.o32 != nullptr) return false;        // training outputs: pm_attn.cu
   const long long items = static_cast<long long>((p.Nq + 2 * A4_BM - 1) / (2 * A4_BM)) * p.H * p.B;
   const int sms = pm_num_sms();
   return (items + sms - 1) / sms <= A4_MAX_ITEMS;
@@ -536,11 +567,17 @@ int pm_attn4_launch(const AttnParams& p, cudaStream_t stream) {
     }
     fn = v->fn;
   }
-  static bool attr_done[PM_MAX_DEVICES] = {};
-  if ((rc = pm_ensure_dyn_smem(fn, A4_SMEM_BYTES, attr_done)) != 0) return rc;
+  static bool attr_done[PM_MAX_DEVICES] = {}, attr_done_train[PM_MAX_DEVICES] = {};
+  Attn4KernelFn kern = fn;
+  if (p.lse != nullptr || p.o32 != nullptr) {
+    kern = attn4_kernel<1, true>;          // (a separate instantiation: the inference kernel's register allocation is untouched)
+    if ((rc = pm_ensure_dyn_smem(kern, A4_SMEM_BYTES, attr_done_train)) != 0) return rc;
+  } else if ((rc = pm_ensure_dyn_smem(fn, A4_SMEM_BYTES, attr_done)) != 0) {
+    return rc;
+  }
   const long long items = static_cast<long long>((p.Nq + 2 * A4_BM - 1) / (2 * A4_BM)) * p.H * p.B;
   const int grid = items < pm_num_sms() ? static_cast<int>(items) : pm_num_sms();
-  fn<<<grid, A4_THREADS, A4_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  kern<<<grid, A4_THREADS, A4_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return static_cast<int>(cudaGetLastError());
 }
 

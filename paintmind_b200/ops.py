@@ -341,9 +341,10 @@ def _workspace(name, nfloats, device):
     return t
 
 
-def attention_train(q, k, v, o, heads, scale, lse, o32=None):
+def attention_train(q, k, v, o, heads, scale, lse, o32=None, prescaled=False):
     """attention() that also writes the base-2 log-sum-exp rows [B, heads, Nq] needed by attention_bwd and, optionally,
-    an fp32 copy of the output ([B, Nq, heads*64] contiguous) for an accurate softmax-backward row term."""
+    an fp32 copy of the output ([B, Nq, heads*64] contiguous) for an accurate softmax-backward row term.  prescaled: q
+    carries scale * log2(e) (see attention()); the matching backward call is attention_bwd(..., scale=ln 2) on the same q."""
     _require_cuda(q, k, v, o, lse, o32)
     args = _lib.AttnArgs()
     args.q, args.k, args.v, args.o = _ptr(q), _ptr(k), _ptr(v), _ptr(o)
@@ -351,6 +352,7 @@ def attention_train(q, k, v, o, heads, scale, lse, o32=None):
     args.bsq, args.bsk, args.bsv, args.bso = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
     args.B, args.H, args.Nq, args.Nk, args.head_dim = q.shape[0], heads, q.shape[1], k.shape[1], 64
     args.scale = float(scale)
+    args.q_prescaled = int(bool(prescaled))
     args.lse, args.lse_ld = _ptr(lse), lse.stride(1)
     if o32 is not None:
         if o32.dtype != torch.float32 or not o32.is_contiguous():

@@ -27,8 +27,10 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .engine import LN_EPS, _RowStats, _fingerprint, run_blocks
+from .engine import LN_EPS, LOG2E, _RowStats, _fingerprint, run_blocks
 from .ops import PM_OUT_F32, PM_OUT_UNPATCH
+
+LN2 = 0.6931471805599453
 
 
 def _t_bf16(w):
@@ -42,7 +44,11 @@ class _BlockBwd:
     def __init__(self, layer, fwd_blk):
         a1, ff = layer.attn1, layer.ffnet
         dev = a1.to_q.weight.device
-        wqkv = torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], dim=0).detach()
+        # the forward runs on PRE-SCALED queries (engine._Block.w_qkv_ps: scale * log2(e) folded into the to_q rows), so the
+        # backward differentiates with respect to q' = c q: dn = dqkv' W'^T uses the same scaled rows, and the to_q rows of the
+        # weight gradient are multiplied by c afterwards (qscale)
+        self.qscale = float(a1.scale) * LOG2E
+        wqkv = torch.cat([a1.to_q.weight.detach().float() * self.qscale, a1.to_k.weight.detach().float(), a1.to_v.weight.detach().float()], dim=0)
         self.w_qkv_t = _t_bf16(wqkv)                                   # [D, 3 inner]
         self.w_o_t = _t_bf16(a1.to_out[0].weight)                     # [inner, D]
         h = ff.w12.weight.shape[0] // 2
@@ -178,9 +184,10 @@ class Stage1TrainEngine:
         ao = torch.empty(M, inner, device=dev, dtype=torch.bfloat16)
         ao32 = torch.empty(B, N, inner, device=dev, dtype=torch.float32)
         lse = ops.lse_buffer(B, H, N, dev)
-        ops.gemm(x, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, **st.consume())
+        ops.gemm(x, blk.w_qkv_ps, qkv, bias=blk.b_qkv_ps, colsum=blk.cs_qkv_ps, **st.consume())
         q3 = qkv.view(B, N, 3 * inner)
-        ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32)
+        ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32,
+                            prescaled=True)
         x_mid = torch.empty_like(x)
         ops.gemm(ao, blk.w_o, x_mid, bias=blk.b_o, res=x, stats_out=st.produce())
         h = self.eng.ws.get("h", (M, blk.hp), torch.bfloat16, dev)
@@ -211,9 +218,10 @@ class Stage1TrainEngine:
             lse = ws.get("lse", (B, H, (N + 127) // 128 * 128), torch.float32, dev)[:, :, :N]
             ao32 = ws.get("ao32", (B, N, inner), torch.float32, dev)
             ops.layernorm(x_in, stats=stats)
-            ops.gemm(x_in, blk.w_qkv, qkv, bias=blk.b_qkv, colsum=blk.cs_qkv, stats=stats)
+            ops.gemm(x_in, blk.w_qkv_ps, qkv, bias=blk.b_qkv_ps, colsum=blk.cs_qkv_ps, stats=stats)
             q3 = qkv.view(B, N, 3 * inner)
-            ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32)
+            ops.attention_train(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao.view(B, N, inner), H, blk.scale, lse, ao32,
+                                prescaled=True)
             ops.gemm(ao, blk.w_o, x_mid, bias=blk.b_o, res=x_in)
         ops.layernorm(x_mid, stats=stats)
         ops.gemm(x_mid, blk.w_12, x12, bias=blk.b_12, colsum=blk.cs_12, stats=stats)          # plain store: gate | value tiles
@@ -248,10 +256,13 @@ class Stage1TrainEngine:
         dqkv = ws.get("dqkv", (M, 3 * inner), bf, dev)
         d3 = dqkv.view(B, N, 3 * inner)
         ops.attention_bwd(q3[..., :inner], q3[..., inner:2 * inner], q3[..., 2 * inner:], ao32, dao.view(B, N, inner), lse,
-                          d3[..., :inner], d3[..., inner:2 * inner], d3[..., 2 * inner:], H, blk.scale)
+                          d3[..., :inner], d3[..., inner:2 * inner], d3[..., 2 * inner:], H, LN2)
+        # (q is pre-scaled: the natural-log logits are ln2 * q' k^T, so `scale` = ln 2 makes the kernel's exp2 argument q' k^T - lse
+        #  and its dq the gradient with respect to q'; dk and dv are the true gradients)
         ops.layernorm(x_in, gamma=bw.g1, beta=bw.b1, y=nbuf)
         wqkv = torch.empty(3 * inner, D, **f32)
         ops.wgrad(dqkv, nbuf, wqkv)
+        wqkv[:inner].mul_(bw.qscale)                         # d/d to_q.weight = c * d/d (c to_q.weight)
         ops.gemm(dqkv, bw.w_qkv_t, dn)
         gb1 = torch.empty(2, D, **f32)
         ops.layernorm_bwd(dn, x_in, bw.g1, dx, gb1, dres=dx_mid, eps=LN_EPS)

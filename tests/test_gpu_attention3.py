@@ -128,3 +128,17 @@ print("CHILD OK")
 """ % (str(root), str(root / "tests"))
     r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, PM_ATTN_PRE="3"), capture_output=True, text=True, timeout=300)
     assert "CHILD OK" in r.stdout, r.stdout[-800:] + r.stderr[-1500:]
+
+
+def test_prescaled_attention_is_batch_invariant(cuda_device):
+    """A row's output bits do not depend on which other work items the CTA processed before it (every item's first key tile is
+    issued with offset 0): the same samples inside a larger batch — several items per CTA, another item -> CTA assignment —
+    give bit-identical outputs."""
+    torch.manual_seed(13)
+    B, N, H = 40, 512, 8
+    q = (torch.randn(B, N, 512, device=cuda_device) * (0.125 * LOG2E)).bfloat16()
+    k = torch.randn(B, N, 512, device=cuda_device).bfloat16()
+    v = torch.randn(B, N, 512, device=cuda_device).bfloat16()
+    full = _run(q, k, v, H)
+    part = _run(q[3:9].contiguous(), k[3:9].contiguous(), v[3:9].contiguous(), H)
+    assert torch.equal(full[3:9], part)

@@ -86,13 +86,10 @@ def test_encode_decode_vs_reference_golden(cuda_device, gold_name):
     with torch.no_grad():
         rec3, loss3 = model(x)
     assert torch.equal(rec3, model.decode(z_q)) and abs(loss3.item() - loss.item()) < 1e-6
-    # with autograd enabled the same call is the generator training forward (unscaled-query attention kernel + saved
-    # tensors): same function, bf16-level differences, a few codes flipped at near-ties (measured: 0 % / 1.8 % of the codes,
-    # mean |rec difference| 0.0022 / 0.0063 — the same size as the flips against the fp32 reference above)
+    # with autograd enabled the same call is the generator training forward (same kernels + saved tensors): bit-identical
     rec4, loss4 = model(x)
-    flips = (model.train_engine().last_indices != idx).float().mean().item()
-    assert rec4.requires_grad and flips < 0.03
-    assert (rec4.detach() - rec3).abs().mean() < 0.01 and abs(loss4.item() - loss3.item()) < 2e-3 * abs(loss3.item())
+    assert rec4.requires_grad and torch.equal(model.train_engine().last_indices, idx)
+    assert torch.equal(rec4.detach(), rec3) and abs(loss4.item() - loss3.item()) < 1e-6
 
 
 def test_vq_microbench_vs_reference_golden(cuda_device):
