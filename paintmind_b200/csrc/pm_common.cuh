@@ -100,20 +100,68 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 #ifndef PM_MBAR_TIMEOUT_CYCLES
 #define PM_MBAR_TIMEOUT_CYCLES 4000000000ll  // ~2 s at 1.9 GHz
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// What a failed poll costs matters (profiles/r02_attention.md): the waiting warps share their scheduler with working ones.
+// PM_MBAR_FLAVOR (build-time A/B, -DPM_MBAR_FLAVOR=n through PM_NVCC_EXTRA): 0 = poll + clock watchdog (ptxas if-converts the
+// clock test into every spin: ~12 instructions per failed poll, which acts as a back-off), 1 = lean poll with a poll-count
+// watchdog (5 instructions per failed poll: measured SLOWER, 6751 -> 6276 images/s), 2 = flavour 0 + nanosleep after a failed
+// poll, 3 = flavour 0 with a suspend-time hint on try_wait.
+#ifndef PM_MBAR_FLAVOR
+#define PM_MBAR_FLAVOR 0
+#endif
+#ifndef PM_MBAR_SLEEP_NS
+#define PM_MBAR_SLEEP_NS 32
+#endif
+#ifndef PM_MBAR_HINT_NS
+#define PM_MBAR_HINT_NS 2000
+#endif
+__device__ __forceinline__ uint32_t mbar_poll_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+#if PM_MBAR_FLAVOR == 3
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(PM_MBAR_HINT_NS))
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#endif
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_impl(uint32_t bar, uint32_t parity) {
+  if (mbar_poll_a(bar, parity)) return;
+#if PM_MBAR_FLAVOR == 1
+  for (uint32_t spins = 0; spins < (1u << 26); ++spins)
+    if (mbar_poll_a(bar, parity)) return;
+  __trap();
+#else
   const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_poll_a(bar, parity)) {
+#if PM_MBAR_FLAVOR == 2
+    __nanosleep(PM_MBAR_SLEEP_NS);
+#endif
     if ((++spins & 0x3ffu) == 0 && clock64() - t0 > PM_MBAR_TIMEOUT_CYCLES) {
 #ifdef PM_MBAR_PRINTF
-      printf("pm: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
-             blockIdx.y, threadIdx.x, smem_u32(bar), parity);
+      printf("pm: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
 #endif
       __trap();
     }
   }
+#endif
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_impl(smem_u32(bar), parity); }
 
 // named barrier among a subset of warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
@@ -378,20 +426,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait_a(uint32_t bar, uint32_t parit
       : "memory");
   return ok;
 }
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_a(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait_a(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > PM_MBAR_TIMEOUT_CYCLES) {
-#ifdef PM_MBAR_PRINTF
-      printf("pm: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, bar, parity);
-#endif
-      __trap();
-    }
-  }
-}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) { mbar_wait_impl(bar, parity); }
 __device__ __forceinline__ void tma_load_3d_a(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
                                               int32_t c0, int32_t c1, int32_t c2) {
   asm volatile(

@@ -56,7 +56,7 @@ def main():
             env["PM_ATTN_PRE"] = "3"
             env["PM_ATTN3_VARIANT"] = c
         try:
-            r = subprocess.run([sys.executable, "-c", CHILD % (str(ROOT), pre)], env=env, capture_output=True, text=True, timeout=240)
+            r = subprocess.run([sys.executable, "-c", CHILD % (str(ROOT), pre)], env=env, capture_output=True, text=True, timeout=int(os.environ.get("PM_AB_TIMEOUT", "240")))
             out = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
             print(f"variant {c:8s} {out[0] if out else 'FAILED: ' + r.stderr[-800:]}", flush=True)
         except subprocess.TimeoutExpired:
