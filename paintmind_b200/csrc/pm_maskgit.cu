@@ -384,6 +384,10 @@ maskgit_sample_smem_kernel(const MaskgitParams p_in) {
 // staged 0.707 ms, streaming insertion 1.80 ms; a register-resident variant (256 threads holding the row in
 // registers, next row prefetched under the selection) was tried and measured SLOWER (0.695 ms) — the per-row critical
 // path (shuffle-serial tau / top-k selection), not the staging, is what limits these kernels.
+// Round 2: in-kernel phase timers (cycles per row and block, six blocks per SM): load 2,000 | pass 1 + tau 1,800 | pass 2 4,100 |
+// selection 4,300.  Moving the selection to a FIFTH warp with double-buffered candidate lists (named-barrier hand-over, ids[row]
+// fetched ahead, workers already staging the next row; bit-identical results, tests green) measured 0.641 ms against 0.540 ms
+// for this kernel at six blocks per SM (0.727 ms at five): the phases stretch when more warps run — dropped (profiles/r02_membound.txt).
 // ---------------------------------------------------------------------------------------------
 constexpr int MGB_WARPS = 4;
 constexpr int MGB_CAND = 64;      // per warp

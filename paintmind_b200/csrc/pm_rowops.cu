@@ -3,6 +3,8 @@
 #include "pm_common.cuh"
 #include "pm_kernels.h"
 
+#include <stdlib.h>
+
 namespace pm {
 
 // ----------------------------------------------------------------------------------------------
@@ -118,75 +120,99 @@ constexpr int LN_MAX_VEC = 8;   // 8 x (32 lanes x 8 elts) = 2048 columns
 // D = 512 compiles to a 2-vector kernel with ~4x the occupancy of the generic 8-vector one (measured: 1.9 -> TB/s).
 // Round 2: every warp handles TWO rows at once (2 NV 16-byte loads in flight per lane instead of NV): at D = 512 one row per
 // warp left the kernel at 4.0 TB/s, latency-bound on 32 bytes in flight per lane (profiles/r01_membound.txt).
+// Round 2, second pass: ncu showed the two-rows-per-warp kernel ISSUE-bound, not latency-bound (issue slots 76 % busy, 371 warp
+// instructions per 512-wide row, 1.2 M local loads: 64 registers spilled; four rows per warp changed nothing).  Now: packed
+// f32x2 arithmetic in every pass (sum, variance, affine output, statistics of the rounded output: ~7 instead of ~14 instructions
+// per element) and three instead of four resident blocks so that the fp32 row stays in registers without spills.
+__device__ __forceinline__ void ln_unpack4(const uint4& u, float2 (&f)[4]) {
+  f[0] = make_float2(bf16lo_to_f32(u.x), bf16hi_to_f32(u.x));
+  f[1] = make_float2(bf16lo_to_f32(u.y), bf16hi_to_f32(u.y));
+  f[2] = make_float2(bf16lo_to_f32(u.z), bf16hi_to_f32(u.z));
+  f[3] = make_float2(bf16lo_to_f32(u.w), bf16hi_to_f32(u.w));
+}
+
 template <int MODE, int NV>
-__global__ void __launch_bounds__(256, NV <= 2 ? 4 : 1)
+__global__ void __launch_bounds__(256, NV <= 2 ? 3 : 1)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int D, float eps,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int64_t ldy, float* __restrict__ stats) {
+  constexpr int R = 2;                           // rows per warp
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int row0 = 2 * warp;
+  const int row0 = R * warp;
   if (row0 >= M) return;
-  const bool two = row0 + 1 < M;
+  const int nrows = M - row0 < R ? M - row0 : R;
   const int nvec = D >> 3;                      // 16-byte vectors per row
-  float v[2][NV][8];
-  uint4 u[2][NV];
+  float2 v[R][NV][4];
+  {
+    uint4 u[R][NV];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = i * 32 + lane;
-      u[r][i] = make_uint4(0u, 0u, 0u, 0u);
-      if (vi < nvec && (r == 0 || two)) u[r][i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row0 + r) * ldx + vi * 8);
-    }
-  float sum[2] = {0.0f, 0.0f};
+      for (int i = 0; i < NV; ++i) {
+        const int vi = i * 32 + lane;
+        u[r][i] = make_uint4(0u, 0u, 0u, 0u);
+        if (vi < nvec && r < nrows) u[r][i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row0 + r) * ldx + vi * 8);
+      }
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      v[r][i][0] = bf16lo_to_f32(u[r][i].x); v[r][i][1] = bf16hi_to_f32(u[r][i].x);
-      v[r][i][2] = bf16lo_to_f32(u[r][i].y); v[r][i][3] = bf16hi_to_f32(u[r][i].y);
-      v[r][i][4] = bf16lo_to_f32(u[r][i].z); v[r][i][5] = bf16hi_to_f32(u[r][i].z);
-      v[r][i][6] = bf16lo_to_f32(u[r][i].w); v[r][i][7] = bf16hi_to_f32(u[r][i].w);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sum[r] += v[r][i][k];          // lanes beyond the row hold zeros
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
-    sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+      for (int i = 0; i < NV; ++i) ln_unpack4(u[r][i], v[r][i]);
   }
-  float mean[2], rstd[2], sq[2] = {0.0f, 0.0f};
+  float mean[R], rstd[R];
+  {
+    float2 s2[R];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    mean[r] = sum[r] / static_cast<float>(D);
+    for (int r = 0; r < R; ++r) {
+      s2[r] = make_float2(0.0f, 0.0f);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      for (int i = 0; i < NV; ++i)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float d = v[r][i][k] - mean[r];
-          sq[r] = fmaf(d, d, sq[r]);
+        for (int k = 0; k < 4; ++k) s2[r] = __fadd2_rn(s2[r], v[r][i][k]);       // lanes beyond the row hold zeros
+    }
+    float sum[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) sum[r] = s2[r].x + s2[r].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+    float sq[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] = sum[r] / static_cast<float>(D);
+      const float2 nm = make_float2(-mean[r], -mean[r]);
+      float2 q2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (i * 32 + lane < nvec) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 d = __fadd2_rn(v[r][i][k], nm);
+            q2 = __ffma2_rn(d, d, q2);
+          }
         }
       }
+      sq[r] = q2.x + q2.y;
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], o);
-    sq[1] += __shfl_xor_sync(0xffffffffu, sq[1], o);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(sq[r] / static_cast<float>(D) + eps);
   }
-  rstd[0] = rsqrtf(sq[0] / static_cast<float>(D) + eps);
-  rstd[1] = rsqrtf(sq[1] / static_cast<float>(D) + eps);
   if (MODE == 0) {
     if (lane == 0) {
-      *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0)) = make_float2(mean[0], rstd[0]);
-      if (two) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + 1)) = make_float2(mean[1], rstd[1]);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r < nrows) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + r)) = make_float2(mean[r], rstd[r]);
     }
     return;
   }
-  float ysum[2] = {0.0f, 0.0f};
+  float2 ys2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) ys2[r] = make_float2(0.0f, 0.0f);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = i * 32 + lane;
@@ -195,57 +221,152 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int D,
       const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
       const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8);
       const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float2 g[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+      const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (r == 1 && !two) break;
+      for (int r = 0; r < R; ++r) {
+        const float2 nm = make_float2(-mean[r], -mean[r]);
+        const float2 rs = make_float2(rstd[r], rstd[r]);
         uint32_t pk[4];
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          const float a0 = (v[r][i][k] - mean[r]) * rstd[r] * g[k] + bb[k];
-          const float a1 = (v[r][i][k + 1] - mean[r]) * rstd[r] * g[k + 1] + bb[k + 1];
-          pk[k >> 1] = pack_bf16x2(a0, a1);
+        for (int k = 0; k < 4; ++k) {
+          // ((x - mean) * rstd) * gamma + beta, each step rounded as before
+          const float2 a = __ffma2_rn(__fmul2_rn(__fadd2_rn(v[r][i][k], nm), rs), g[k], bb[k]);
+          pk[k] = pack_bf16x2(a.x, a.y);
           // statistics of the ROUNDED output (what the next GEMM will actually read); v is reused to hold it
-          v[r][i][k] = bf16lo_to_f32(pk[k >> 1]);
-          v[r][i][k + 1] = bf16hi_to_f32(pk[k >> 1]);
-          ysum[r] += v[r][i][k] + v[r][i][k + 1];
+          v[r][i][k] = make_float2(bf16lo_to_f32(pk[k]), bf16hi_to_f32(pk[k]));
+          ys2[r] = __fadd2_rn(ys2[r], v[r][i][k]);
         }
-        *reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * ldy + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (r < nrows) *reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * ldy + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }
   if (stats != nullptr) {
+    float ysum[R];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ysum[0] += __shfl_xor_sync(0xffffffffu, ysum[0], o);
-      ysum[1] += __shfl_xor_sync(0xffffffffu, ysum[1], o);
-    }
-    float ysq[2] = {0.0f, 0.0f};
-    const float ymean[2] = {ysum[0] / static_cast<float>(D), ysum[1] / static_cast<float>(D)};
+    for (int r = 0; r < R; ++r) ysum[r] = ys2[r].x + ys2[r].y;
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) ysum[r] += __shfl_xor_sync(0xffffffffu, ysum[r], o);
+    float ysq[R], ymean[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      ymean[r] = ysum[r] / static_cast<float>(D);
+      const float2 nm = make_float2(-ymean[r], -ymean[r]);
+      float2 q2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const int vi = i * 32 + lane;
-        if (vi < nvec) {
+        if (i * 32 + lane < nvec) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float d = v[r][i][k] - ymean[r];
-            ysq[r] = fmaf(d, d, ysq[r]);
+          for (int k = 0; k < 4; ++k) {
+            const float2 d = __fadd2_rn(v[r][i][k], nm);
+            q2 = __ffma2_rn(d, d, q2);
           }
         }
       }
+      ysq[r] = q2.x + q2.y;
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ysq[0] += __shfl_xor_sync(0xffffffffu, ysq[0], o);
-      ysq[1] += __shfl_xor_sync(0xffffffffu, ysq[1], o);
-    }
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) ysq[r] += __shfl_xor_sync(0xffffffffu, ysq[r], o);
     if (lane == 0) {
-      *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0)) = make_float2(ymean[0], rsqrtf(ysq[0] / static_cast<float>(D) + eps));
-      if (two)
-        *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + 1)) = make_float2(ymean[1], rsqrtf(ysq[1] / static_cast<float>(D) + eps));
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r < nrows)
+          *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + r)) = make_float2(ymean[r], rsqrtf(ysq[r] / static_cast<float>(D) + eps));
     }
+  }
+}
+
+// Fast path for D = 256 / 512 / 1024 (compile-time D, no tail guards): HALF a warp per row, so that the two rows of a warp share
+// every shuffle of the four reductions (4 steps instead of 5, one instruction for both rows), and the divisions by D fold into
+// multiplications.  ~330 executed instructions per warp (two rows) against ~740 for the generic kernel above, which ncu showed
+// issue-bound (76 % of the issue slots, 4.5 TB/s whatever the number of rows in flight).
+template <int MODE, int D>
+__global__ void __launch_bounds__(256, D <= 512 ? 4 : 2)
+layernorm_half_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, float eps,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      __nv_bfloat16* __restrict__ y, int64_t ldy, float* __restrict__ stats) {
+  constexpr int NV = D / 128;                    // 16-byte vectors per lane (16 lanes per row)
+  constexpr float inv_d = 1.0f / static_cast<float>(D);      // exact: D is a power of two
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int hl = lane & 15;
+  const int row = 2 * warp + (lane >> 4);
+  if (2 * warp >= M) return;
+  const bool ok = row < M;
+  float2 v[NV][4];
+  {
+    uint4 u[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      u[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) u[i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + (i * 16 + hl) * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ln_unpack4(u[i], v[i]);
+  }
+  auto half_sum = [](float a) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+  };
+  float2 s2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s2 = __fadd2_rn(s2, v[i][k]);
+  const float mean = half_sum(s2.x + s2.y) * inv_d;
+  float2 nm = make_float2(-mean, -mean);
+  float2 q2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d = __fadd2_rn(v[i][k], nm);
+      q2 = __ffma2_rn(d, d, q2);
+    }
+  const float rstd = rsqrtf(half_sum(q2.x + q2.y) * inv_d + eps);
+  if (MODE == 0) {
+    if (hl == 0 && ok) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row)) = make_float2(mean, rstd);
+    return;
+  }
+  const float2 rs = make_float2(rstd, rstd);
+  float2 ys2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 16 + hl) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float2 g[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+    const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __ffma2_rn(__fmul2_rn(__fadd2_rn(v[i][k], nm), rs), g[k], bb[k]);
+      pk[k] = pack_bf16x2(a.x, a.y);
+      v[i][k] = make_float2(bf16lo_to_f32(pk[k]), bf16hi_to_f32(pk[k]));     // the ROUNDED output: what the next GEMM reads
+      ys2 = __fadd2_rn(ys2, v[i][k]);
+    }
+    if (ok) *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * ldy + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (stats != nullptr) {
+    const float ymean = half_sum(ys2.x + ys2.y) * inv_d;
+    nm = make_float2(-ymean, -ymean);
+    q2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 d = __fadd2_rn(v[i][k], nm);
+        q2 = __ffma2_rn(d, d, q2);
+      }
+    const float yr = rsqrtf(half_sum(q2.x + q2.y) * inv_d + eps);
+    if (hl == 0 && ok) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row)) = make_float2(ymean, yr);
   }
 }
 
@@ -300,11 +421,31 @@ static void launch_ln(const void* x, int64_t ldx, int M, int D, float eps, const
                                                             gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), ldy, stats);
 }
 
+template <int D>
+static void launch_ln_half(const void* x, int64_t ldx, int M, float eps, const float* gamma, const float* beta, void* y, int64_t ldy,
+                           float* stats, cudaStream_t stream) {
+  const int blocks = (M + 15) / 16;              // 8 warps x 2 rows per block
+  if (y == nullptr)
+    layernorm_half_kernel<0, D><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, eps, nullptr, nullptr,
+                                                            nullptr, 0, stats);
+  else
+    layernorm_half_kernel<1, D><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, eps, gamma, beta,
+                                                            reinterpret_cast<__nv_bfloat16*>(y), ldy, stats);
+}
+
 int pm_layernorm_launch(const void* x, int64_t ldx, int M, int D, float eps, const float* gamma,
                         const float* beta, void* y, int64_t ldy, float* stats, cudaStream_t stream) {
   if (x == nullptr || M <= 0 || D <= 0 || (D % 8) != 0 || D > LN_MAX_VEC * 256 || (ldx % 8) != 0) return PM_ERR_INVALID;
   if (y == nullptr && stats == nullptr) return PM_ERR_INVALID;
   if (y != nullptr && (gamma == nullptr || beta == nullptr || (ldy % 8) != 0)) return PM_ERR_INVALID;
+  static int generic = -1;                       // PM_LN_GENERIC=1: the generic kernel for every D (A/B aid)
+  if (generic < 0) generic = getenv("PM_LN_GENERIC") != nullptr ? 1 : 0;
+  if (!generic && (D == 256 || D == 512 || D == 1024)) {
+    if (D == 256) launch_ln_half<256>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
+    else if (D == 512) launch_ln_half<512>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
+    else launch_ln_half<1024>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
+    return static_cast<int>(cudaGetLastError());
+  }
   if (D <= 256) launch_ln<1>(x, ldx, M, D, eps, gamma, beta, y, ldy, stats, stream);
   else if (D <= 512) launch_ln<2>(x, ldx, M, D, eps, gamma, beta, y, ldy, stats, stream);
   else if (D <= 1024) launch_ln<4>(x, ldx, M, D, eps, gamma, beta, y, ldy, stats, stream);

@@ -16,6 +16,11 @@ mp = ROOT / "MEASURED_PEAKS.json"
 if mp.exists():
     peak = json.loads(mp.read_text())["hbm_gbs"]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # 512 MB > 126 MB L2
+flush.zero_()
+CLEAN = "--dirty" not in sys.argv
+# L2 flush: writing a buffer (the round-1 method, `--dirty`) leaves up to 126 MB of DIRTY lines whose write-back is then charged to the
+# timed kernel (~20 us: 16 % of a 0.12 ms kernel).  Default now: the write is followed by a read-only pass over the same 512 MB,
+# which evicts the dirty lines before the timer starts and leaves clean ones.
 
 
 def timeit(fn, iters=10):
@@ -24,6 +29,8 @@ def timeit(fn, iters=10):
     ts = []
     for _ in range(iters):
         flush.zero_()                                                # evict L2
+        if CLEAN:
+            flush.view(torch.int32).max()                            # read-only pass: dirty lines written back, clean lines left
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -50,6 +57,24 @@ y = torch.empty_like(x)
 gam, bet = torch.ones(D, device=dev), torch.zeros(D, device=dev)
 st = torch.empty(M, 2, device=dev)
 report("layernorm [262144,512] bf16 (norm_pre)", 2 * M * D * 2 + M * 8, timeit(lambda: ops.layernorm(x, gamma=gam, beta=bet, y=y, stats=st)))
+
+# calibration: what a plain copy of the same 268 MB -> 268 MB reaches under this harness (launch + ramp + tail included)
+report("(calibration) torch copy_ [262144,512] bf16", 2 * M * D * 2, timeit(lambda: y.copy_(x)))
+if "--big" in sys.argv:
+    xb = torch.randn(4 * M, D, device=dev, generator=g).bfloat16()
+    yb = torch.empty_like(xb)
+    stb = torch.empty(4 * M, 2, device=dev)
+    report("layernorm [1048576,512] bf16", 2 * 4 * M * D * 2 + 4 * M * 8, timeit(lambda: ops.layernorm(xb, gamma=gam, beta=bet, y=yb, stats=stb)))
+    report("(calibration) torch copy_ [1048576,512] bf16", 2 * 4 * M * D * 2, timeit(lambda: yb.copy_(xb)))
+    del xb, yb, stb
+
+# layernorm backward (generator training step): reads dn, x, dres (bf16), writes dx (bf16) + per-column sums
+dn = torch.randn(M, D, device=dev, generator=g).bfloat16()
+dres = torch.randn(M, D, device=dev, generator=g).bfloat16()
+dx = torch.empty_like(x)
+dgb = torch.empty(2, D, device=dev)
+report("layernorm_bwd [262144,512] bf16 (+dres)", 4 * M * D * 2, timeit(lambda: ops.layernorm_bwd(dn, x, gam, dx, dgb, dres=dres)))
+del dn, dres, dx
 
 # patchify fp32 NCHW -> bf16 patches: 12 B/px in, 6 B/px out
 img = torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1
