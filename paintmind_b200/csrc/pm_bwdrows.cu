@@ -29,17 +29,25 @@ __device__ __forceinline__ float warp_sum(float v) {
 // (mu, rstd) are recomputed from the row (it is in registers anyway).  Each block walks rows blockIdx.x * 8 + warp,
 // += gridDim.x * 8 and leaves its partial (dgamma | dbeta) in part[blockIdx.x, 2, D]; colreduce_kernel sums the blocks.
 // ----------------------------------------------------------------------------------------------
+// Round 2: gamma lives in registers for the whole launch (ncu on the forward kernel: re-reading parameters per row saturates the
+// L1 data stage, not HBM) and the NEXT row's three vectors per lane (x, dn, dres) are requested before the current row's four
+// dependent reductions — dres used to be loaded behind them.
 template <int NV>
-__global__ void __launch_bounds__(256, NV <= 2 ? 3 : 1)
+__global__ void __launch_bounds__(256, NV <= 2 ? 2 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfloat16* __restrict__ x, int64_t ldx,
               const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres, int64_t ldres,
               __nv_bfloat16* __restrict__ dx, int64_t lddx, int M, int D, float eps, float* __restrict__ part) {
   extern __shared__ float red[];                 // [8][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  float ag[NV][8], ab[NV][8];
+  float ag[NV][8], ab[NV][8], gm[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
+    const bool in = i * 32 + lane < nvec;
+    const float4 g0 = in ? __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 g1 = in ? __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
+    gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       ag[i][k] = 0.f;
@@ -47,22 +55,34 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfl
     }
   }
   const float inv_d = 1.0f / static_cast<float>(D);
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    float xv[NV][8], gv[NV][8];
-    float s = 0.f;
+  const int step = gridDim.x * 8;
+  uint4 ux[NV], ug[NV], ur[NV];
+  auto load_row = [&](int row) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = i * 32 + lane;
-      if (vi < nvec) {
-        unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + vi * 8), xv[i]);
-        unpack8(*reinterpret_cast<const uint4*>(dn + static_cast<size_t>(row) * lddn + vi * 8), gv[i]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += xv[i][k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) xv[i][k] = 0.f, gv[i][k] = 0.f;
+      ux[i] = ug[i] = ur[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (vi < nvec && row < M) {
+        ux[i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + vi * 8);
+        ug[i] = *reinterpret_cast<const uint4*>(dn + static_cast<size_t>(row) * lddn + vi * 8);
+        if (dres != nullptr) ur[i] = *reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * ldres + vi * 8);
       }
     }
+  };
+  int row = blockIdx.x * 8 + warp;
+  load_row(row);
+  for (; row < M; row += step) {
+    float xv[NV][8], gv[NV][8], rv[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      unpack8(ux[i], xv[i]);
+      unpack8(ug[i], gv[i]);
+      unpack8(ur[i], rv[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += xv[i][k];              // lanes beyond the row hold zeros
+    }
+    load_row(row + step);                                      // in flight under this row's reductions
     const float mu = warp_sum(s) * inv_d;
     float sq = 0.f;
 #pragma unroll
@@ -79,17 +99,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfl
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (i * 32 + lane < nvec) {
-        // gamma is re-read per row (L1-resident, 2 x 16 B per lane): keeping it in registers cost an occupancy step
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 8 + 4));
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float xh = (xv[i][k] - mu) * rstd;
           const float dnv = gv[i][k];
           ag[i][k] = fmaf(dnv, xh, ag[i][k]);
           ab[i][k] += dnv;
-          const float g = dnv * gm[k];
+          const float g = dnv * gm[i][k];
           xv[i][k] = xh;
           gv[i][k] = g;
           c1 += g;
@@ -106,10 +122,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfl
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = rstd * (gv[i][k] - c1 - xv[i][k] * c2);
         if (dres != nullptr) {
-          float r[8];
-          unpack8(*reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * ldres + vi * 8), r);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += r[k];
+          for (int k = 0; k < 8; ++k) o[k] += rv[i][k];
         }
         *reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * lddx + vi * 8) = pack8(o);
       }
@@ -138,7 +152,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dn, int64_t lddn, const __nv_bfl
 }
 
 int pm_ln_bwd_blocks(int M) {
-  const int want = (M + 7) / 8, cap = 6 * pm_num_sms();
+  const int want = (M + 7) / 8, cap = 2 * pm_num_sms();       // two resident blocks per SM: one wave
   return want < cap ? want : cap;
 }
 

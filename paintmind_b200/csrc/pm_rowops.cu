@@ -280,93 +280,154 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, int D,
   }
 }
 
-// Fast path for D = 256 / 512 / 1024 (compile-time D, no tail guards): HALF a warp per row, so that the two rows of a warp share
-// every shuffle of the four reductions (4 steps instead of 5, one instruction for both rows), and the divisions by D fold into
-// multiplications.  ~330 executed instructions per warp (two rows) against ~740 for the generic kernel above, which ncu showed
-// issue-bound (76 % of the issue slots, 4.5 TB/s whatever the number of rows in flight).
+// Fast paths for D = 256 / 512 / 1024 (compile-time D, no tail guards, divisions by D fold into exact multiplications).
+// Tried first: HALF a warp per row (the two rows of a warp share every shuffle; 330 executed instructions per two rows against 740
+// for the generic kernel) — 0.117 ms one-shot, 0.111 ms persistent with prefetch: no better than the generic 0.119-0.121 ms.
+// ncu on the variants above: L1/TEX throughput 94 % — every output element drags 8 bytes of gamma / beta through the L1 data
+// stage next to its 2 + 2 bytes of row data.  This kernel is PERSISTENT (a fixed grid walks the rows) so that a lane keeps the
+// gamma / beta of ITS columns in registers for the whole launch, and it requests the next rows' vectors before it works on the
+// current ones.  One warp per row (R rows per trip), compile-time D.
 template <int MODE, int D>
-__global__ void __launch_bounds__(256, D <= 512 ? 4 : 2)
-layernorm_half_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, float eps,
-                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                      __nv_bfloat16* __restrict__ y, int64_t ldy, float* __restrict__ stats) {
-  constexpr int NV = D / 128;                    // 16-byte vectors per lane (16 lanes per row)
+__global__ void __launch_bounds__(256, 2)
+layernorm_reg_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int M, float eps,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ y, int64_t ldy, float* __restrict__ stats) {
+  constexpr int NV = D / 256;                    // 16-byte vectors per lane
+  constexpr int R = D <= 512 ? 2 : 1;            // rows per trip
   constexpr float inv_d = 1.0f / static_cast<float>(D);      // exact: D is a power of two
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int hl = lane & 15;
-  const int row = 2 * warp + (lane >> 4);
-  if (2 * warp >= M) return;
-  const bool ok = row < M;
-  float2 v[NV][4];
-  {
-    uint4 u[NV];
+  const int nwarps = static_cast<int>(gridDim.x * blockDim.x) >> 5;
+  int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R;
+  if (row0 >= M) return;
+  float2 g[NV][4], bb[NV][4];
+  if (MODE == 1) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      u[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok) u[i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + (i * 16 + hl) * 8);
+      const int c = (i * 32 + lane) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      g[i][0] = make_float2(g0.x, g0.y); g[i][1] = make_float2(g0.z, g0.w); g[i][2] = make_float2(g1.x, g1.y); g[i][3] = make_float2(g1.z, g1.w);
+      bb[i][0] = make_float2(b0.x, b0.y); bb[i][1] = make_float2(b0.z, b0.w); bb[i][2] = make_float2(b1.x, b1.y); bb[i][3] = make_float2(b1.z, b1.w);
     }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) ln_unpack4(u[i], v[i]);
   }
-  auto half_sum = [](float a) {
+  auto load_rows = [&](uint4 (&u)[R][NV], int r0) {
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    return a;
-  };
-  float2 s2 = make_float2(0.0f, 0.0f);
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s2 = __fadd2_rn(s2, v[i][k]);
-  const float mean = half_sum(s2.x + s2.y) * inv_d;
-  float2 nm = make_float2(-mean, -mean);
-  float2 q2 = make_float2(0.0f, 0.0f);
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 d = __fadd2_rn(v[i][k], nm);
-      q2 = __ffma2_rn(d, d, q2);
-    }
-  const float rstd = rsqrtf(half_sum(q2.x + q2.y) * inv_d + eps);
-  if (MODE == 0) {
-    if (hl == 0 && ok) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row)) = make_float2(mean, rstd);
-    return;
-  }
-  const float2 rs = make_float2(rstd, rstd);
-  float2 ys2 = make_float2(0.0f, 0.0f);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 16 + hl) * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c);
-    const float4 g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(beta + c + 4);
-    const float2 g[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
-    const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-    uint32_t pk[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 a = __ffma2_rn(__fmul2_rn(__fadd2_rn(v[i][k], nm), rs), g[k], bb[k]);
-      pk[k] = pack_bf16x2(a.x, a.y);
-      v[i][k] = make_float2(bf16lo_to_f32(pk[k]), bf16hi_to_f32(pk[k]));     // the ROUNDED output: what the next GEMM reads
-      ys2 = __fadd2_rn(ys2, v[i][k]);
-    }
-    if (ok) *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * ldy + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  }
-  if (stats != nullptr) {
-    const float ymean = half_sum(ys2.x + ys2.y) * inv_d;
-    nm = make_float2(-ymean, -ymean);
-    q2 = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 d = __fadd2_rn(v[i][k], nm);
-        q2 = __ffma2_rn(d, d, q2);
+      for (int i = 0; i < NV; ++i) {
+        u[r][i] = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + r < M) u[r][i] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r0 + r) * ldx + (i * 32 + lane) * 8);
       }
-    const float yr = rsqrtf(half_sum(q2.x + q2.y) * inv_d + eps);
-    if (hl == 0 && ok) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row)) = make_float2(ymean, yr);
+  };
+  uint4 u[R][NV];
+  load_rows(u, row0);
+  for (; row0 < M; row0 += nwarps * R) {
+    float2 v[R][NV][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) ln_unpack4(u[r][i], v[r][i]);
+    if (row0 + nwarps * R < M) load_rows(u, row0 + nwarps * R);       // next trip's rows: in flight under this trip's arithmetic
+    float mean[R], rstd[R];
+    {
+      float sum[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float2 s2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) s2 = __fadd2_rn(s2, v[r][i][k]);
+        sum[r] = s2.x + s2.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < R; ++r) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+      float sq[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        mean[r] = sum[r] * inv_d;
+        const float2 nm = make_float2(-mean[r], -mean[r]);
+        float2 q2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 d = __fadd2_rn(v[r][i][k], nm);
+            q2 = __ffma2_rn(d, d, q2);
+          }
+        sq[r] = q2.x + q2.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < R; ++r) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(sq[r] * inv_d + eps);
+    }
+    if (MODE == 0) {
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (row0 + r < M) *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + r)) = make_float2(mean[r], rstd[r]);
+      }
+      continue;
+    }
+    float ysum[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float2 nm = make_float2(-mean[r], -mean[r]);
+      const float2 rs = make_float2(rstd[r], rstd[r]);
+      float2 ys2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __ffma2_rn(__fmul2_rn(__fadd2_rn(v[r][i][k], nm), rs), g[i][k], bb[i][k]);
+          pk[k] = pack_bf16x2(a.x, a.y);
+          v[r][i][k] = make_float2(bf16lo_to_f32(pk[k]), bf16hi_to_f32(pk[k]));   // the ROUNDED output: what the next GEMM reads
+          ys2 = __fadd2_rn(ys2, v[r][i][k]);
+        }
+        if (row0 + r < M)
+          *reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * ldy + (i * 32 + lane) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      ysum[r] = ys2.x + ys2.y;
+    }
+    if (stats != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < R; ++r) ysum[r] += __shfl_xor_sync(0xffffffffu, ysum[r], o);
+      float ysq[R], ymean[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        ymean[r] = ysum[r] * inv_d;
+        const float2 nm = make_float2(-ymean[r], -ymean[r]);
+        float2 q2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 d = __fadd2_rn(v[r][i][k], nm);
+            q2 = __ffma2_rn(d, d, q2);
+          }
+        ysq[r] = q2.x + q2.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < R; ++r) ysq[r] += __shfl_xor_sync(0xffffffffu, ysq[r], o);
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (row0 + r < M)
+            *reinterpret_cast<float2*>(stats + 2 * static_cast<size_t>(row0 + r)) = make_float2(ymean[r], rsqrtf(ysq[r] * inv_d + eps));
+      }
+    }
   }
 }
 
@@ -422,15 +483,23 @@ static void launch_ln(const void* x, int64_t ldx, int M, int D, float eps, const
 }
 
 template <int D>
-static void launch_ln_half(const void* x, int64_t ldx, int M, float eps, const float* gamma, const float* beta, void* y, int64_t ldy,
-                           float* stats, cudaStream_t stream) {
-  const int blocks = (M + 15) / 16;              // 8 warps x 2 rows per block
+static void launch_ln_reg(const void* x, int64_t ldx, int M, float eps, const float* gamma, const float* beta, void* y, int64_t ldy,
+                          float* stats, cudaStream_t stream) {
+  constexpr int R = D <= 512 ? 2 : 1;
+  const int want = (M + 8 * R - 1) / (8 * R);    // 8 warps x R rows per block and trip
+  static int per_sm = -1;                        // PM_LN_BLOCKS=<blocks per SM> (tuning aid)
+  if (per_sm < 0) {
+    const char* env = getenv("PM_LN_BLOCKS");
+    per_sm = env != nullptr ? atoi(env) : 2;
+  }
+  const int cap = pm_num_sms() * per_sm;
+  const int blocks = want < cap ? want : cap;
   if (y == nullptr)
-    layernorm_half_kernel<0, D><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, eps, nullptr, nullptr,
-                                                            nullptr, 0, stats);
+    layernorm_reg_kernel<0, D><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, eps, nullptr, nullptr,
+                                                           nullptr, 0, stats);
   else
-    layernorm_half_kernel<1, D><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, eps, gamma, beta,
-                                                            reinterpret_cast<__nv_bfloat16*>(y), ldy, stats);
+    layernorm_reg_kernel<1, D><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, eps, gamma, beta,
+                                                           reinterpret_cast<__nv_bfloat16*>(y), ldy, stats);
 }
 
 int pm_layernorm_launch(const void* x, int64_t ldx, int M, int D, float eps, const float* gamma,
@@ -441,9 +510,9 @@ int pm_layernorm_launch(const void* x, int64_t ldx, int M, int D, float eps, con
   static int generic = -1;                       // PM_LN_GENERIC=1: the generic kernel for every D (A/B aid)
   if (generic < 0) generic = getenv("PM_LN_GENERIC") != nullptr ? 1 : 0;
   if (!generic && (D == 256 || D == 512 || D == 1024)) {
-    if (D == 256) launch_ln_half<256>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
-    else if (D == 512) launch_ln_half<512>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
-    else launch_ln_half<1024>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
+    if (D == 256) launch_ln_reg<256>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
+    else if (D == 512) launch_ln_reg<512>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
+    else launch_ln_reg<1024>(x, ldx, M, eps, gamma, beta, y, ldy, stats, stream);
     return static_cast<int>(cudaGetLastError());
   }
   if (D <= 256) launch_ln<1>(x, ldx, M, D, eps, gamma, beta, y, ldy, stats, stream);
