@@ -47,8 +47,16 @@ __device__ __forceinline__ float norm_u8(uint32_t u) {
   return __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);                        // Normalize(mean 0.5, std 0.5)
 }
 
-// The 256 possible results are tabulated once per block (bf16 bits in shared memory): the two IEEE divisions per
-// byte made the first version compute-bound (2.2 TB/s); with the table the kernel is a byte shuffle.
+// The two IEEE divisions per byte made the first version compute-bound (2.2 TB/s); the second tabulated the 256 possible
+// results in shared memory — 24 two-byte look-ups per thread at random addresses, i.e. ~4-way bank conflicts on each: that table
+// was what held the kernel at 62 % of the copy peak.  Now: bf16(fma(u, fp32(2/255), -1)) — it equals bf16 of the reference's chain
+// for ALL 256 byte values (tests/test_host_logic.py::test_u8_normalise_formula_is_exact checks the 256 cases), one PRMT + one
+// FFMA per byte: the byte goes into the mantissa of 2^23 (0x4B0000uu = 8388608 + u) and the fused multiply-add removes the
+// offset again exactly (8388608 * c + 1 = 65794.0078125 is representable).
+__device__ __forceinline__ float norm_u8_fast(uint32_t word, int byte) {
+  const float f = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + static_cast<uint32_t>(byte)));     // 8388608 + u
+  return __fmaf_rn(f, 0.007843137718737125f, -65794.0078125f);
+}
 //
 // Round 2: one block iteration = one ROW OF PATCHES (8 image rows x W pixels in, gw patch rows of 384 B out — contiguous in
 // `out`).  Thread (y, tw) converts 8 pixels into three 16-byte chunks as before, but drops them into a shared-memory image of
@@ -59,13 +67,7 @@ constexpr int PU8_PITCH = 400;                 // bytes per patch in the staging
 
 __global__ void __launch_bounds__(256)
 patchify8_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
-  __shared__ uint16_t lut[256];
   extern __shared__ __align__(16) uint8_t stage[];          // [gw][PU8_PITCH]
-  {
-    const __nv_bfloat16 h = __float2bfloat16_rn(norm_u8(threadIdx.x));
-    lut[threadIdx.x] = *reinterpret_cast<const uint16_t*>(&h);
-  }
-  __syncthreads();
   const int gw = W >> 3, gh = H >> 3;
   const int work = gw * 8;                                   // (y, tw) pairs of one patch row
   const int chunks = gw * 24;                                // 16-byte chunks of its output
@@ -85,15 +87,15 @@ patchify8_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__
   for (; pr < n_rows; pr += gridDim.x) {
     if (active) {
       const uint32_t wd[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
-      uint32_t v[3][8];
+      float v[3][8];
 #pragma unroll
-      for (int i = 0; i < 24; ++i) v[i % 3][i / 3] = lut[(wd[i >> 2] >> ((i & 3) * 8)) & 0xffu];
+      for (int i = 0; i < 24; ++i) v[i % 3][i / 3] = norm_u8_fast(wd[i >> 2], i & 3);
       uint8_t* dst = stage + tw0 * PU8_PITCH + kh0 * 16;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         uint4 o;
-        o.x = v[c][0] | (v[c][1] << 16); o.y = v[c][2] | (v[c][3] << 16);
-        o.z = v[c][4] | (v[c][5] << 16); o.w = v[c][6] | (v[c][7] << 16);
+        o.x = pack_bf16x2(v[c][0], v[c][1]); o.y = pack_bf16x2(v[c][2], v[c][3]);
+        o.z = pack_bf16x2(v[c][4], v[c][5]); o.w = pack_bf16x2(v[c][6], v[c][7]);
         *reinterpret_cast<uint4*>(dst + c * 128) = o;
       }
     }

@@ -190,3 +190,23 @@ def test_model_copies_build_their_own_engine():
     assert c._engine is None and c.engine() is not m.engine() and c.engine().model is c
     r = pickle.loads(pickle.dumps(m))
     assert r._engine is None and all(torch.equal(a, b) for a, b in zip(r.state_dict().values(), m.state_dict().values()))
+
+
+def test_u8_normalise_formula_is_exact():
+    """patchify8_u8 (csrc/pm_rowops.cu::norm_u8_fast) replaces the reference's ingest chain — T.ToTensor() = u / 255, then
+    T.Normalize(0.5, 0.5) = (t - 0.5) / 0.5, both fp32 (reference utils/transform.py:17-18) — by one fused multiply-add on
+    0x4B0000uu = 8388608 + u.  The two must agree after bf16 rounding for every one of the 256 byte values."""
+    import numpy as np
+    import torch
+    u = np.arange(256, dtype=np.float32)
+    t = (u / np.float32(255.0)).astype(np.float32)
+    ref = torch.from_numpy(((t - np.float32(0.5)) / np.float32(0.5)).astype(np.float32)).bfloat16()
+    c = np.float32(0.007843137718737125)
+    assert c == np.float32(2.0 / 255.0)
+    k = np.float64(8388608.0) * np.float64(c) + 1.0
+    assert k == 65794.0078125 and np.float32(k) == k            # the offset the FMA removes is representable
+    magic = (np.uint32(0x4B000000) | np.arange(256, dtype=np.uint32)).view(np.float32)
+    assert np.array_equal(magic, np.float32(8388608.0) + u)
+    # the FMA is exact before its single rounding: float64 holds (8388608 + u) * c - k without error (24 + 24 bits)
+    fast = torch.from_numpy((magic.astype(np.float64) * np.float64(c) - k).astype(np.float32)).bfloat16()
+    assert torch.equal(fast.view(torch.int16), ref.view(torch.int16))
