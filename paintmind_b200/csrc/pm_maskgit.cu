@@ -432,43 +432,41 @@ maskgit_sample_block_kernel(const MaskgitParams p_in) {
   };
   for (int row = blockIdx.x; row < p.M; row += gridDim.x) {
     if (threadIdx.x == 0) fetch_row(row);
+    // ids[row] is only needed at the very end of the row, by one lane: fetched now, its global-memory latency used to sit at
+    // the end of the serial selection tail
+    long long id_row = 0;
+    if (threadIdx.x == 0 && p.ids != nullptr) id_row = p.ids[row];
     mbar_wait(bar, phase);
     phase ^= 1;
-    // ---- pass 1: per-thread two largest values (four independent max / min chains, merged at the end) ----
-    float t0 = -INFINITY, t1 = -INFINITY;
+    // ---- pass 1: per-thread maximum (four independent 3-input max chains) ----
+    // Round 2: the thread's SECOND largest value is no longer tracked (three half-rate FMNMX per element, 41 % of the ALU pipe):
+    // the k-th largest of a warp's 32 thread maxima is still a lower bound of the row's k-th largest value (the maxima are 32
+    // distinct elements), only a slightly looser one — a few more candidates reach the lists of pass 2 (capacity 64 per warp).
+    float t0;
     {
-      float u0[4], u1[4];
+      float u0[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { u0[u] = -INFINITY; u1[u] = -INFINITY; }
+      for (int u = 0; u < 4; ++u) u0[u] = -INFINITY;
       for (int c = threadIdx.x; c < nvec; c += MGB_WARPS * 32 * 4) {
         float4 q[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) q[u] = b4[c + MGB_WARPS * 32 * u];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            u1[u] = fmaxf(u1[u], fminf(u0[u], e[t]));
-            u0[u] = fmaxf(u0[u], e[t]);
-          }
+          u0[u] = fmaxf(fmaxf(u0[u], q[u].x), q[u].y);
+          u0[u] = fmaxf(fmaxf(u0[u], q[u].z), q[u].w);
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        t1 = fmaxf(t1, fminf(t0, u0[u]));
-        t0 = fmaxf(t0, u0[u]);
-        t1 = fmaxf(t1, fminf(t0, u1[u]));       // u1[u] <= u0[u] <= t0: only t1 can change
-      }
+      t0 = fmaxf(fmaxf(u0[0], u0[1]), fmaxf(u0[2], u0[3]));
     }
     const float mw = warp_max_f32(t0);
-    // k-th largest of this warp's 64 leaders: a lower bound of the row's k-th largest value
-    float a0 = t0, a1 = t1, tau_w = -INFINITY;
+    // k-th largest of this warp's 32 thread maxima: a lower bound of the row's k-th largest value
+    float a0 = t0, tau_w = -INFINITY;
     for (int r = 0; r < k; ++r) {
       const float bv = warp_max_f32(a0);
       tau_w = bv;
       const unsigned who = __ballot_sync(0xffffffffu, a0 == bv);
-      if (lane == __ffs(who) - 1) { a0 = a1; a1 = -INFINITY; }
+      if (lane == __ffs(who) - 1) a0 = -INFINITY;
     }
     if (lane == 0) {
       sh_f[warp] = mw;
@@ -478,7 +476,9 @@ maskgit_sample_block_kernel(const MaskgitParams p_in) {
     const float m_row = fmaxf(fmaxf(sh_f[0], sh_f[1]), fmaxf(sh_f[2], sh_f[3]));
     const float tau = fmaxf(fmaxf(sh_f[4], sh_f[5]), fmaxf(sh_f[6], sh_f[7]));
     // ---- pass 2: softmax denominator and candidates >= tau ----
-    float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float2 ps2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ps2[u] = make_float2(0.0f, 0.0f);
     int ncand = 0;                                                    // warp-uniform
     float* cv_w = cand_v + warp * MGB_CAND;
     int* ci_w = cand_i + warp * MGB_CAND;
@@ -487,18 +487,23 @@ maskgit_sample_block_kernel(const MaskgitParams p_in) {
       float4 q[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) q[u] = b4[c + MGB_WARPS * 32 * u];
-      bool any = false;
+      // packed f32x2 arithmetic for the exponent argument and the partial sums; one compare per 16 elements (group maximum)
+      float gmax = -INFINITY;
+      const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f), nm2 = make_float2(nm, nm);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float ex;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(e[t], 1.4426950408889634f, nm)));
-          ps[u] += ex;
-          any |= (e[t] >= tau);
-        }
+        const float2 a01 = __ffma2_rn(make_float2(q[u].x, q[u].y), l2e, nm2);
+        const float2 a23 = __ffma2_rn(make_float2(q[u].z, q[u].w), l2e, nm2);
+        float2 e01, e23;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e01.x) : "f"(a01.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e01.y) : "f"(a01.y));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e23.x) : "f"(a23.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e23.y) : "f"(a23.y));
+        ps2[u] = __fadd2_rn(ps2[u], __fadd2_rn(e01, e23));
+        gmax = fmaxf(fmaxf(gmax, q[u].x), q[u].y);
+        gmax = fmaxf(fmaxf(gmax, q[u].z), q[u].w);
       }
+      const bool any = gmax >= tau;
       if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -516,7 +521,7 @@ maskgit_sample_block_kernel(const MaskgitParams p_in) {
         }
       }
     }
-    float ssum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    float ssum = ((ps2[0].x + ps2[0].y) + (ps2[1].x + ps2[1].y)) + ((ps2[2].x + ps2[2].y) + (ps2[3].x + ps2[3].y));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
     if (lane == 0) {
@@ -618,7 +623,7 @@ maskgit_sample_block_kernel(const MaskgitParams p_in) {
         if (p.pred_ids != nullptr) p.pred_ids[row] = pred;
         bool is_mask = true;
         if (p.ids != nullptr) {
-          is_mask = (p.ids[row] == p.mask_id);
+          is_mask = (id_row == p.mask_id);
           if (is_mask) p.ids[row] = pred;
         }
         if (p.scores != nullptr) p.scores[row] = is_mask ? (1.0f - prob) : -1e5f;
