@@ -137,6 +137,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   const uint32_t p_full = s_free + 16;                            // [2][2]  softmax -> MMA: P_t columns of key half kh written
   const uint32_t pv_done = p_full + 32;                           // [2]     MMA -> softmax: O_t += P_t V complete
   const uint32_t tmem_slot_a = pv_done + 16;
+  const uint32_t pass_done = tmem_slot_a + 16;                    //         softmax warps -> everyone: pass 0 complete, redo bitmap final
   uint8_t* const smO = smem_raw + (sO - raw_a);
   float* const smL = reinterpret_cast<float*>(smem_raw + (sL - raw_a));
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot_a - raw_a));
@@ -195,6 +196,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       init(p_full + 16 * t + 8, 4);          // key half 1
       init(pv_done + 8 * t, 1);
     }
+    init(pass_done, 16);                   // one arrival per softmax warp
     fence_mbar_init();
   }
   if (warp == 17) {
@@ -211,7 +213,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     int ic = 0, g = 0;                               // running item / step counters (barrier phases) across both passes
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1) {
-        __syncthreads();                             // pass 0 complete everywhere, bitmap final
+        mbar_wait_a(pass_done, 0);                   // pass 0 complete in every softmax warp, bitmap final
         if (*redo_any == 0) break;
       }
       if (lane == 0) {
@@ -330,7 +332,11 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const bool exact = pass == 1;
       if (pass == 1) {
         if (tile_leader) tma_store_wait_all<0>();    // pass-0 stores of re-run items must not land after the new ones
-        __syncthreads();
+        // (an mbarrier, not a block barrier: the two warp roles would reach it from different program locations, which
+        //  compute-sanitizer's synccheck reports as a divergent barrier)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(pass_done);
+        mbar_wait_a(pass_done, 0);
         if (*redo_any == 0) break;
       }
       for (int i = 0; i < my_items; ++i) {

@@ -110,6 +110,59 @@ patchify8_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__
   }
 }
 
+// fp32 NCHW ingest through the same shared-memory output image (C = 3, W <= 256): the direct kernel above stores 16 bytes every
+// 384 (half-filled sectors: 78 % of the copy peak).  One block iteration = one row of patches: 24 gw items (c, kh, tw) of 8 floats,
+// up to three per thread; the next row's loads are in flight while this one is streamed out.
+__global__ void __launch_bounds__(256)
+patchify8_stage_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  extern __shared__ __align__(16) uint8_t stage[];          // [gw][PU8_PITCH]
+  const int gw = W >> 3, gh = H >> 3;
+  const int items = gw * 24;                                 // (c, kh, tw) pieces of one patch row == 16-byte chunks of its output
+  const long long n_rows = static_cast<long long>(B) * gh;
+  int soff[3];                                               // staging offset of this thread's items (-1: none)
+  size_t goff[3];                                            // source offset within the image, relative to the patch row's first line
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int j = threadIdx.x + 256 * r;
+    const int tw = j % gw, rest = j / gw;
+    const int kh = rest & 7, c = rest >> 3;
+    soff[r] = j < items ? tw * PU8_PITCH + c * 128 + kh * 16 : -1;
+    goff[r] = (static_cast<size_t>(c) * H + kh) * W + tw * 8;
+  }
+  float4 a[3][2];
+  auto load = [&](long long pr) {
+    const int th = static_cast<int>(pr % gh);
+    const int b = static_cast<int>(pr / gh);
+    const float* base = img + (static_cast<size_t>(b) * 3 * H + th * 8) * W;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      if (soff[r] >= 0) {
+        a[r][0] = __ldcs(reinterpret_cast<const float4*>(base + goff[r]));
+        a[r][1] = __ldcs(reinterpret_cast<const float4*>(base + goff[r] + 4));
+      }
+  };
+  long long pr = blockIdx.x;
+  if (pr < n_rows) load(pr);
+  for (; pr < n_rows; pr += gridDim.x) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      if (soff[r] >= 0) {
+        uint4 o;
+        o.x = pack_bf16x2(a[r][0].x, a[r][0].y); o.y = pack_bf16x2(a[r][0].z, a[r][0].w);
+        o.z = pack_bf16x2(a[r][1].x, a[r][1].y); o.w = pack_bf16x2(a[r][1].z, a[r][1].w);
+        *reinterpret_cast<uint4*>(stage + soff[r]) = o;
+      }
+    __syncthreads();
+    if (pr + gridDim.x < n_rows) load(pr + gridDim.x);
+    uint4* gdst = reinterpret_cast<uint4*>(out + static_cast<size_t>(pr) * gw * 192);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int tw = i / 24, ch = i - tw * 24;
+      gdst[i] = *reinterpret_cast<const uint4*>(stage + tw * PU8_PITCH + ch * 16);
+    }
+    __syncthreads();
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // LayerNorm over rows of a bf16 [M, D] matrix (D % 8 == 0, D <= 2048), eps inside the sqrt,
 // biased variance — nn.LayerNorm semantics (stage1/layers.py:49,51,89,128).
@@ -451,6 +504,15 @@ int pm_cast_launch(const float* src, void* dst, long long n, cudaStream_t stream
 
 int pm_patchify_launch(const float* img, void* out, int B, int C, int H, int W, int P, cudaStream_t stream) {
   if (img == nullptr || out == nullptr || P != 8 || (H % 8) != 0 || (W % 8) != 0 || B <= 0 || C <= 0) return PM_ERR_INVALID;
+  static int direct = -1;                                         // PM_PATCHIFY_DIRECT=1: the direct kernel for every shape (A/B aid)
+  if (direct < 0) direct = getenv("PM_PATCHIFY_DIRECT") != nullptr ? 1 : 0;
+  if (!direct && C == 3 && W <= 256) {
+    long long nb = static_cast<long long>(B) * (H / 8);           // one patch row per block iteration
+    const long long cap = static_cast<long long>(pm_num_sms()) * 8;
+    if (nb > cap) nb = cap;
+    patchify8_stage_kernel<<<static_cast<unsigned>(nb), 256, (W / 8) * PU8_PITCH, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, H, W);
+    return static_cast<int>(cudaGetLastError());
+  }
   const long long total = static_cast<long long>(B) * C * H * (W / 8);
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;

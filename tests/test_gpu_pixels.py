@@ -37,6 +37,20 @@ def _model(cfg_name, sd, dev):
     return m.to(dev).eval()
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 256, 256), (3, 3, 64, 32), (1, 3, 8, 8), (5, 3, 24, 256), (2, 1, 32, 32), (1, 3, 16, 512)])
+def test_patchify_fp32_vs_unfold(cuda_device, B, C, H, W):
+    """pm_patchify8 (stage1/layers.py:82-83: the stride-8 patch conv's im2col, K order c, kh, kw) against torch unfold: the staged
+    kernel (C = 3, W <= 256; ragged last block iterations, non-square images) and the direct kernel (other shapes)."""
+    g = torch.Generator().manual_seed(11)
+    img = (torch.rand(B, C, H, W, generator=g) * 2 - 1).to(cuda_device)
+    M = B * (H // 8) * (W // 8)
+    got = torch.full((M, C * 64), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    ops.patchify8(img, got)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.unfold(img, kernel_size=8, stride=8).transpose(1, 2).reshape(M, C * 64).to(torch.bfloat16)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+
+
 @pytest.mark.parametrize("B,S", [(1, 64), (3, 256), (2, 8)])
 def test_patchify_u8_bit_exact(cuda_device, B, S):
     g = torch.Generator().manual_seed(5)
