@@ -388,6 +388,8 @@ maskgit_sample_smem_kernel(const MaskgitParams p_in) {
 // selection 4,300.  Moving the selection to a FIFTH warp with double-buffered candidate lists (named-barrier hand-over, ids[row]
 // fetched ahead, workers already staging the next row; bit-identical results, tests green) measured 0.641 ms against 0.540 ms
 // for this kernel at six blocks per SM (0.727 ms at five): the phases stretch when more warps run — dropped (profiles/r02_membound.txt).
+// Eight warps per row buffer (half the per-thread work of both passes): 0.85 ms — 67 registers x 256 threads leave three resident
+// blocks instead of six; a single polling warp per block (the others asleep in the block barrier) changed neither variant.
 // ---------------------------------------------------------------------------------------------
 constexpr int MGB_WARPS = 4;
 constexpr int MGB_CAND = 64;      // per warp
