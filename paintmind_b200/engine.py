@@ -187,6 +187,10 @@ def run_blocks(blocks, x, st, B, N, ws, context_kv=None, ctx_len=0):
     M, D = x.shape
     dev = x.device
     for li, blk in enumerate(blocks):
+        if ops.NVTX:
+            if li:
+                torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push(f"pm.block{li}")
         inner = blk.inner
         qkv = ws.get("qkv", (M, 3 * inner), torch.bfloat16, dev)
         ao = ws.get("ao", (M, inner), torch.bfloat16, dev)
@@ -212,6 +216,8 @@ def run_blocks(blocks, x, st, B, N, ws, context_kv=None, ctx_len=0):
         h = ws.get("h", (M, blk.hp), torch.bfloat16, dev)
         ops.gemm(x, blk.w_12, h, bias=blk.b_12, colsum=blk.cs_12, swiglu=True, **st.consume())
         ops.gemm(h, blk.w_3, x, bias=blk.b_3, res=x, stats_out=st.produce())
+    if ops.NVTX and len(blocks):
+        torch.cuda.nvtx.range_pop()
     return x
 
 
@@ -293,6 +299,7 @@ class Stage1Engine:
 
     # -- encoder -------------------------------------------------------------------------------
     @ops.on_device_of
+    @ops.nvtx_phase("pm.encoder")
     def run_encoder(self, img):
         """img fp32 NCHW in [-1, 1] -> tokens bf16 [B, N, D]  (Encoder.forward, layers.py:106-112).
         A uint8 [B, H, W, 3] tensor (decoded pixels) is also accepted: the reference's ingest transform
@@ -333,6 +340,7 @@ class Stage1Engine:
         return x.view(B, N, D)
 
     @ops.on_device_of
+    @ops.nvtx_phase("pm.encode")
     def encode(self, img):
         m = self.model
         if img.shape[0] == 0:
@@ -346,8 +354,9 @@ class Stage1Engine:
         M = B * N
         dev = x.device
         z = self.ws.get("z", (M, m.quantize.e_dim), torch.float32, dev)
-        ops.gemm(x.view(M, D), self.w_prev, z, bias=self.b_prev, out_mode=PM_OUT_F32, bn=32)   # prev_quant
-        r = m.quantize.quantize_2d(z, want_split=False)
+        with ops.nvtx_range("pm.quantize"):
+            ops.gemm(x.view(M, D), self.w_prev, z, bias=self.b_prev, out_mode=PM_OUT_F32, bn=32)   # prev_quant
+            r = m.quantize.quantize_2d(z, want_split=False)
         loss = (r["sse"] * ((1.0 + m.quantize.beta) / (M * m.quantize.e_dim))).to(torch.float32).reshape(())
         return r["zq"].view(B, N, -1), loss, r["idx"].view(B, N)
 
@@ -380,6 +389,7 @@ class Stage1Engine:
         return img
 
     @ops.on_device_of
+    @ops.nvtx_phase("pm.decode")
     def decode(self, z, pixels=False):
         """z [B, N, 32] -> image [B, 3, H, W] in [-1, 1]  (VQModel.decode, vqmodel.py:27-30);
         pixels=True -> uint8 [B, H, W, 3] = restore(decode(z)) (reconstruct.py:11-16)."""
@@ -417,6 +427,7 @@ class Stage1Engine:
         return self._decode_tokens_inplace(x, st, B, N, dev, pixels)
 
     @ops.on_device_of
+    @ops.nvtx_phase("pm.decode_from_indice")
     def decode_from_indice(self, indice, pixels=False):
         """ids [B, N] int64 -> image  (vqmodel.py:38-41, quantize.py:40-44)."""
         self._ensure_packed()
@@ -434,6 +445,7 @@ class Stage1Engine:
         return self._decode_split(zs, B, N, dev, pixels)
 
     @ops.on_device_of
+    @ops.nvtx_phase("pm.decoder")
     def run_decoder_tokens(self, tokens):
         """Decoder.forward on [B, N, D] tokens (layers.py:145-152) -> un-clamped?  NOTE: the fused
         store clamps to [-1, 1] exactly like VQModel.decode; Decoder.forward alone is only reachable

@@ -316,6 +316,10 @@ class Pipeline(nn.Module):
             masked_r = mask_schedule(progress)
             cur_temp = temperature * (1 - step / timesteps)
             keep = (step % save_interval == 0)
+            if ops.NVTX:
+                if step:
+                    torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push(f"pm.maskgit_step{step}")
             if use_graph:
                 g["graph"].replay()
                 img = self.vqgan.decode_from_indice(g["pred_ids"]) if (keep or decode_every_step) else None
@@ -332,5 +336,7 @@ class Pipeline(nn.Module):
                     host.copy_(img, non_blocking=True)
                 img.record_stream(side)
                 imgs.append(host)
+        if ops.NVTX and timesteps > 0:
+            torch.cuda.nvtx.range_pop()
         side.synchronize()
         return imgs

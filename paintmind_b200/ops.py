@@ -6,6 +6,7 @@ RuntimeError on failure.  PyTorch only provides device memory and streams here.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -19,6 +20,48 @@ PROFILE = None
 PROFILE_ONLY = None   # optional set of op names (key[0]): only these are bracketed by events (bench.py times the dominant kernel
                       # inside its timed region this way and the full per-kernel table in a separate, untimed pass)
 LAUNCHES = 0          # kernels launched through this module (bench.py's gpu_launches)
+
+
+# Optional NVTX ranges (PM_NVTX=1): phases of the engine (encode / quantize / decode / block i / MaskGIT step) and every op
+# push a range on the calling thread, so that `ncu --nvtx --nvtx-include "pm.encode/"` or an nsys timeline can be cut by phase.
+# Off by default: a range costs ~1 us of host time per op.
+NVTX = os.environ.get("PM_NVTX", "0") not in ("", "0")
+
+
+class nvtx_range:
+    """with ops.nvtx_range("pm.encode"): ...   (no-op unless PM_NVTX=1)"""
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx_phase(name):
+    """Decorator form of nvtx_range for engine entry points."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*a, **k):
+            if not NVTX:
+                return fn(*a, **k)
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapper
+    return deco
 
 
 def _prof_begin():

@@ -14,8 +14,12 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from pathlib import Path
+
 from conftest import check_weight_checksums, load_golden, seeded_vqgan
 from paintmind_b200.utils import synthetic
+
+ROOT = Path(__file__).resolve().parents[1]
 
 pytestmark = pytest.mark.gpu
 
@@ -293,3 +297,28 @@ def test_graphed_encode_decode_matches_eager_and_follows_weight_updates(cuda_dev
     assert torch.equal(rec_g, model.decode(model.encode(x2)[0]))
     with pytest.raises(RuntimeError):
         run(x1[:2])
+
+
+def test_nvtx_ranges_do_not_change_results(cuda_device):
+    """PM_NVTX=1 (phase / block / op ranges for ncu --nvtx or a timeline) in a child process: same indices and loss bits."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import seeded_vqgan\n"
+        "import paintmind_b200 as pm\n"
+        "from paintmind_b200.utils import synthetic\n"
+        "cfg, sd, _ = seeded_vqgan('vit-tiny-test', 7)\n"
+        "m = pm.create_model(arch='vqgan', version='vit-tiny-test', pretrained=False); m.load_state_dict(sd); m = m.cuda().eval()\n"
+        "x = synthetic.make_images(3, cfg['enc']['image_size'], seed=5).cuda()\n"
+        "z, loss, idx = m.encode(x); rec = m.decode(z); torch.cuda.synchronize()\n"
+        "print('RES', int(idx.sum()), loss.item().hex(), float(rec.double().sum()))\n"
+    ) % (str(ROOT), str(ROOT / "tests"))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, PM_NVTX=flag)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("RES")][0])
+    assert outs[0] == outs[1]

@@ -210,3 +210,26 @@ def test_u8_normalise_formula_is_exact():
     # the FMA is exact before its single rounding: float64 holds (8388608 + u) * c - k without error (24 + 24 bits)
     fast = torch.from_numpy((magic.astype(np.float64) * np.float64(c) - k).astype(np.float32)).bfloat16()
     assert torch.equal(fast.view(torch.int16), ref.view(torch.int16))
+
+
+def test_nvtx_ranges_are_opt_in(monkeypatch):
+    """ops.nvtx_range / nvtx_phase (tracing) do nothing unless PM_NVTX=1 and keep results and exceptions intact."""
+    from paintmind_b200 import ops
+    assert ops.NVTX is False or isinstance(ops.NVTX, bool)
+    calls = []
+    monkeypatch.setattr(ops, "NVTX", False)
+
+    @ops.nvtx_phase("pm.test")
+    def f(a, b=2):
+        calls.append((a, b))
+        return a + b
+    assert f(1, b=3) == 4 and calls == [(1, 3)]
+    with ops.nvtx_range("pm.test") as r:
+        assert r.name == "pm.test"
+
+    @ops.nvtx_phase("pm.raises")
+    def g():
+        raise ValueError("x")
+    import pytest
+    with pytest.raises(ValueError):
+        g()
