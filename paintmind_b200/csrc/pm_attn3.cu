@@ -252,7 +252,10 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     int ic = 0, g = 0;                               // running item / step counters (barrier phases) across both passes
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1) {
-        mbar_wait_a(pass_done, 0);                   // pass 0 complete in every softmax warp, bitmap final
+        // pass 0 complete in every softmax warp, bitmap final.  One lane per role warp polls (a warp without a role would
+        // otherwise poll from the first cycle of the kernel and take issue slots from the softmax warps of its scheduler)
+        if (lane == 0 && (warp <= 10 || PV2)) mbar_wait_a(pass_done, 0);
+        __syncwarp();
         if (*redo_any == 0) break;
       }
       if (lane == 0) {

@@ -67,6 +67,28 @@ __device__ __forceinline__ float2 a4_exp2_poly2(float2 a) {
 }
 __device__ __forceinline__ float a4_bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// Every polling thread takes issue slots from the four softmax warps of its scheduler (measured: tight try_wait / test_wait loops in
+// the two MMA issuer threads 0.649 -> 0.758 ms; an idle warp polling for the whole kernel +2 %).  The TMA producer runs three stages
+// ahead and is latency-insensitive: it sleeps PM_A4_PROD_SLEEP ns after a failed poll (0.7603 -> 0.7565 ms sustained with 200,
+// 0.7587 with 1000).  The same idea on the MMA issuers (a nanosleep between issuing a step and polling for the next) is a loss:
+// 300 ns in the P.V issuer 0.786 ms, 700 ns 0.880 ms — their wake-up latency is on the critical path (profiles/r02_attention.md).
+#ifndef PM_A4_PROD_SLEEP
+#define PM_A4_PROD_SLEEP 200
+#endif
+__device__ __forceinline__ void a4_issuer_wait(uint32_t bar, uint32_t parity) { mbar_wait_a(bar, parity); }
+__device__ __forceinline__ void a4_producer_wait(uint32_t bar, uint32_t parity) {
+#if PM_A4_PROD_SLEEP > 0
+  if (mbar_try_wait_a(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar, parity)) {
+    __nanosleep(PM_A4_PROD_SLEEP);
+    if (clock64() - t0 > PM_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+#else
+  mbar_wait_a(bar, parity);
+#endif
+}
+
 struct A4Item {
   int qb, h, b;
 };
@@ -213,7 +235,10 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     int ic = 0, g = 0;                               // running item / step counters (barrier phases) across both passes
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1) {
-        mbar_wait_a(pass_done, 0);                   // pass 0 complete in every softmax warp, bitmap final
+        // pass 0 complete in every softmax warp, bitmap final.  One lane per role warp polls (a warp without a role would
+        // otherwise poll from the first cycle of the kernel and take issue slots from the softmax warps of its scheduler)
+        if (lane == 0 && warp <= 18) mbar_wait_a(pass_done, 0);
+        __syncwarp();
         if (*redo_any == 0) break;
       }
       if (lane == 0) {
@@ -223,17 +248,17 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             if (pass == 1 && ((redo_bits[i >> 5] >> (i & 31)) & 1u) == 0) continue;
             const A4Item it = a4_item(blockIdx.x + i * gridDim.x, n_qb, p.H);
             const int qs = ic % A4_Q_STAGES;
-            mbar_wait_a(q_empty + 8 * qs, ((ic / A4_Q_STAGES) & 1) ^ 1);
+            a4_producer_wait(q_empty + 8 * qs, ((ic / A4_Q_STAGES) & 1) ^ 1);
             mbar_arrive_expect_tx_a(q_full + 8 * qs, 2 * A4_TILE_BYTES);
             tma_load_3d_a(sQ + (2 * qs) * A4_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * A4_D, it.qb * 2 * A4_BM, it.b);
             tma_load_3d_a(sQ + (2 * qs + 1) * A4_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * A4_D, it.qb * 2 * A4_BM + A4_BM, it.b);
             for (int j = 0; j < n_kv; ++j, ++g) {
               const int st = g % A4_KV_STAGES;
               const uint32_t ph = ((g / A4_KV_STAGES) & 1) ^ 1;
-              mbar_wait_a(k_empty + 8 * st, ph);
+              a4_producer_wait(k_empty + 8 * st, ph);
               mbar_arrive_expect_tx_a(k_full + 8 * st, A4_TILE_BYTES);
               tma_load_3d_a(sK + st * A4_TILE_BYTES, &tmK, k_full + 8 * st, it.h * A4_D, j * A4_BN, it.b);
-              mbar_wait_a(v_empty + 8 * st, ph);
+              a4_producer_wait(v_empty + 8 * st, ph);
               mbar_arrive_expect_tx_a(v_full + 8 * st, A4_TILE_BYTES);
               tma_load_3d_a(sV + st * A4_TILE_BYTES, &tmV, v_full + 8 * st, it.h * A4_D, j * A4_BN, it.b);
             }
@@ -250,14 +275,14 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             const int qs = ic % A4_Q_STAGES;
             for (int j = 0; j < n_kv; ++j, ++g) {
               const int ks = g % A4_KV_STAGES;
-              if (j == 0) mbar_wait_a(q_full + 8 * qs, (ic / A4_Q_STAGES) & 1);
-              mbar_wait_a(k_full + 8 * ks, (g / A4_KV_STAGES) & 1);
+              if (j == 0) a4_issuer_wait(q_full + 8 * qs, (ic / A4_Q_STAGES) & 1);
+              a4_issuer_wait(k_full + 8 * ks, (g / A4_KV_STAGES) & 1);
               const uint64_t dk = umma_desc_sw128(sK + ks * A4_TILE_BYTES);
               const uint64_t db = (j == n_kv - 1) ? d_blast : d_bfull;
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
                 // S_t of the previous step has been read by all 8 warps and A_t holds the offsets for this step
-                if (g > 0) mbar_wait_a(s_free + 8 * t, (g - 1) & 1);
+                if (g > 0) a4_issuer_wait(s_free + 8 * t, (g - 1) & 1);
                 tc_fence_after();
                 const uint64_t dq = umma_desc_sw128(sQ + (2 * qs + t) * A4_TILE_BYTES);
 #pragma unroll
@@ -267,6 +292,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               }
               umma_commit_a(k_empty + 8 * ks);
               if (j == n_kv - 1) umma_commit_a(q_empty + 8 * qs);
+
             }
             ++ic;
           }
@@ -279,20 +305,20 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             if (pass == 1 && ((redo_bits[i >> 5] >> (i & 31)) & 1u) == 0) continue;
             for (int j = 0; j < n_kv; ++j, ++g) {
               const int vs = g % A4_KV_STAGES;
-              mbar_wait_a(v_full + 8 * vs, (g / A4_KV_STAGES) & 1);
+              a4_issuer_wait(v_full + 8 * vs, (g / A4_KV_STAGES) & 1);
               const uint64_t dv = umma_desc_sw128(sV + vs * A4_TILE_BYTES);
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
                 // keys 0-63: the kh = 0 warps (which also did any rescaling of O_t) are done.  On the first step of an item the
                 // first MMA OVERWRITES O_t, whose previous contents the kh = 1 warps may still be reading out: wait for both.
-                mbar_wait_a(p_full + 16 * t, g & 1);
-                if (j == 0) mbar_wait_a(p_full + 16 * t + 8, g & 1);
+                a4_issuer_wait(p_full + 16 * t, g & 1);
+                if (j == 0) a4_issuer_wait(p_full + 16 * t + 8, g & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                   umma_ts(tO[t], tP[t] + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0 ? 1u : 0u);
                 if (j != 0) {
-                  mbar_wait_a(p_full + 16 * t + 8, g & 1);
+                  a4_issuer_wait(p_full + 16 * t + 8, g & 1);
                   tc_fence_after();
                 }
 #pragma unroll
