@@ -325,9 +325,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const float nrmu = -rstd * mu;        // LN fold: rstd * (acc - mu * colsum) + bias == acc * rstd + (nrmu * colsum + bias)
       const float* pos_row = nullptr;
       if (p.pos != nullptr && row_ok) pos_row = p.pos + static_cast<size_t>(row % p.pos_rows) * p.ld_pos;
+      // ONE epilogue warp polls the accumulator's mbarrier, the other seven sleep in the named barrier that follows: a polling
+      // warp costs issue slots and power for as long as the main loop of the tile runs (PM_GEMM_EPI_POLL_ALL=1: all eight poll)
+#ifdef PM_GEMM_EPI_POLL_ALL
       named_bar_sync(1, 256);
-
       mbar_wait(&tfull_bar[as], aphase);
+#else
+      if (ew == 0) mbar_wait(&tfull_bar[as], aphase);
+      named_bar_sync(1, 256);
+#endif
       tc_fence_after();
       const uint32_t tacc = tmem_base + tmem_lane + as * BN;
 
