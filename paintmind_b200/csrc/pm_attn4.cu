@@ -76,6 +76,17 @@ __device__ __forceinline__ float a4_bf16_round(float x) { return __bfloat162floa
 #define PM_A4_PROD_SLEEP 200
 #endif
 __device__ __forceinline__ void a4_issuer_wait(uint32_t bar, uint32_t parity) { mbar_wait_a(bar, parity); }
+// The service warps run their role loops CONVERGED (all 32 lanes wait and compute descriptors in the uniform datapath) and one
+// elected lane issues the TMA / MMA / commit instructions, instead of lane 0 running the whole loop in divergent code (where
+// every tcgen05.mma costs ~16 instructions of R2UR / PLOP3 / ELECT plumbing on the critical path): 0.7623 -> 0.7431 ms
+// sustained (-DPM_A4_LANE0=1 restores the old form).
+#ifndef PM_A4_LANE0
+#define A4_SERVICE_LANES true
+#define A4_ONE if (elect_one())
+#else
+#define A4_SERVICE_LANES (lane == 0)
+#define A4_ONE
+#endif
 __device__ __forceinline__ void a4_producer_wait(uint32_t bar, uint32_t parity) {
 #if PM_A4_PROD_SLEEP > 0
   if (mbar_try_wait_a(bar, parity)) return;
@@ -237,11 +248,11 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (pass == 1) {
         // pass 0 complete in every softmax warp, bitmap final.  One lane per role warp polls (a warp without a role would
         // otherwise poll from the first cycle of the kernel and take issue slots from the softmax warps of its scheduler)
-        if (lane == 0 && warp <= 18) mbar_wait_a(pass_done, 0);
+        if (A4_SERVICE_LANES && warp <= 18) mbar_wait_a(pass_done, 0);
         __syncwarp();
         if (*redo_any == 0) break;
       }
-      if (lane == 0) {
+      if (A4_SERVICE_LANES) {
         if (warp == 16) {
           // ===================================== TMA producer ======================================
           for (int i = 0; i < my_items; ++i) {
@@ -249,18 +260,24 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             const A4Item it = a4_item(blockIdx.x + i * gridDim.x, n_qb, p.H);
             const int qs = ic % A4_Q_STAGES;
             a4_producer_wait(q_empty + 8 * qs, ((ic / A4_Q_STAGES) & 1) ^ 1);
-            mbar_arrive_expect_tx_a(q_full + 8 * qs, 2 * A4_TILE_BYTES);
-            tma_load_3d_a(sQ + (2 * qs) * A4_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * A4_D, it.qb * 2 * A4_BM, it.b);
-            tma_load_3d_a(sQ + (2 * qs + 1) * A4_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * A4_D, it.qb * 2 * A4_BM + A4_BM, it.b);
+            A4_ONE {
+              mbar_arrive_expect_tx_a(q_full + 8 * qs, 2 * A4_TILE_BYTES);
+              tma_load_3d_a(sQ + (2 * qs) * A4_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * A4_D, it.qb * 2 * A4_BM, it.b);
+              tma_load_3d_a(sQ + (2 * qs + 1) * A4_TILE_BYTES, &tmQ, q_full + 8 * qs, it.h * A4_D, it.qb * 2 * A4_BM + A4_BM, it.b);
+            }
             for (int j = 0; j < n_kv; ++j, ++g) {
               const int st = g % A4_KV_STAGES;
               const uint32_t ph = ((g / A4_KV_STAGES) & 1) ^ 1;
               a4_producer_wait(k_empty + 8 * st, ph);
-              mbar_arrive_expect_tx_a(k_full + 8 * st, A4_TILE_BYTES);
-              tma_load_3d_a(sK + st * A4_TILE_BYTES, &tmK, k_full + 8 * st, it.h * A4_D, j * A4_BN, it.b);
+              A4_ONE {
+                mbar_arrive_expect_tx_a(k_full + 8 * st, A4_TILE_BYTES);
+                tma_load_3d_a(sK + st * A4_TILE_BYTES, &tmK, k_full + 8 * st, it.h * A4_D, j * A4_BN, it.b);
+              }
               a4_producer_wait(v_empty + 8 * st, ph);
-              mbar_arrive_expect_tx_a(v_full + 8 * st, A4_TILE_BYTES);
-              tma_load_3d_a(sV + st * A4_TILE_BYTES, &tmV, v_full + 8 * st, it.h * A4_D, j * A4_BN, it.b);
+              A4_ONE {
+                mbar_arrive_expect_tx_a(v_full + 8 * st, A4_TILE_BYTES);
+                tma_load_3d_a(sV + st * A4_TILE_BYTES, &tmV, v_full + 8 * st, it.h * A4_D, j * A4_BN, it.b);
+              }
             }
             ++ic;
           }
@@ -285,13 +302,17 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
                 if (g > 0) a4_issuer_wait(s_free + 8 * t, (g - 1) & 1);
                 tc_fence_after();
                 const uint64_t dq = umma_desc_sw128(sQ + (2 * qs + t) * A4_TILE_BYTES);
+                A4_ONE {
 #pragma unroll
-                for (int k = 0; k < A4_D / 16; ++k) umma_ss(tS[t], dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-                umma_ss(tS[t], d_a[t], db, idesc_qk, 1u);
-                umma_commit_a(s_full + 8 * t);
+                  for (int k = 0; k < A4_D / 16; ++k) umma_ss(tS[t], dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+                  umma_ss(tS[t], d_a[t], db, idesc_qk, 1u);
+                  umma_commit_a(s_full + 8 * t);
+                  if (t == 1) {
+                    umma_commit_a(k_empty + 8 * ks);
+                    if (j == n_kv - 1) umma_commit_a(q_empty + 8 * qs);
+                  }
+                }
               }
-              umma_commit_a(k_empty + 8 * ks);
-              if (j == n_kv - 1) umma_commit_a(q_empty + 8 * qs);
 
             }
             ++ic;
@@ -314,18 +335,22 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
                 a4_issuer_wait(p_full + 16 * t, g & 1);
                 if (j == 0) a4_issuer_wait(p_full + 16 * t + 8, g & 1);
                 tc_fence_after();
+                A4_ONE {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_ts(tO[t], tP[t] + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_ts(tO[t], tP[t] + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                }
                 if (j != 0) {
                   a4_issuer_wait(p_full + 16 * t + 8, g & 1);
                   tc_fence_after();
                 }
+                A4_ONE {
 #pragma unroll
-                for (int kk = 4; kk < 8; ++kk) umma_ts(tO[t], tP[t] + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, 1u);
-                umma_commit_a(pv_done + 8 * t);
+                  for (int kk = 4; kk < 8; ++kk) umma_ts(tO[t], tP[t] + 8 * kk, dv + kk * (2048 >> 4), idesc_pv, 1u);
+                  umma_commit_a(pv_done + 8 * t);
+                  if (t == 1) umma_commit_a(v_empty + 8 * vs);
+                }
               }
-              umma_commit_a(v_empty + 8 * vs);
             }
           }
         }
