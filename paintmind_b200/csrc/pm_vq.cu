@@ -177,8 +177,17 @@ vq_exact4_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Service warps run CONVERGED and an elected lane issues TMA / MMA / commit (PM_VQ_LANE0=1: the old divergent lane-0 loops, in
+  // which every tcgen05.mma costs ~16 instructions of uniform-register plumbing — see pm_attn4.cu)
+#ifdef PM_VQ_LANE0
+#define VQ_SERVICE_LANES (lane == 0)
+#define VQ_ONE
+#else
+#define VQ_SERVICE_LANES true
+#define VQ_ONE if (elect_one())
+#endif
   if (warp == 0) {
-    if (lane == 0) {
+    if (VQ_SERVICE_LANES) {
       int st = 0;
       uint32_t ph = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -186,8 +195,10 @@ vq_exact4_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
         const int code0 = split * codes_per_split;
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(&b_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&b_full[st], VQ_B_BYTES);
-          tma_load_2d(smB + st * VQ_B_BYTES, &tmB, &b_full[st], 0, code0 + t * VQ_BN);
+          VQ_ONE {
+            mbar_arrive_expect_tx(&b_full[st], VQ_B_BYTES);
+            tma_load_2d(smB + st * VQ_B_BYTES, &tmB, &b_full[st], 0, code0 + t * VQ_BN);
+          }
           if (++st == VQ_BSTAGES) { st = 0; ph ^= 1; }
         }
       }
@@ -195,7 +206,7 @@ vq_exact4_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
   } else if (warp == 1 || warp == 10) {
     // two MMA issuer threads, one per 128-row half: the 128x128x16 MMAs are short (64 tensor cycles), a single
     // issuing thread cannot keep the pipe fed
-    if (lane == 0) {
+    if (VQ_SERVICE_LANES) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, VQ_BN, 0, 0);
       const int rh = (warp == 1) ? 0 : 1;
       int st = 0;
@@ -213,14 +224,16 @@ vq_exact4_kernel(const __grid_constant__ CUtensorMap tmB, const VqParams p) {
           tc_fence_after();
           const uint64_t db = umma_desc_sw128(smem_u32(smB + st * VQ_B_BYTES));
           const uint32_t tacc = tmem_base + (as * 2 + rh) * VQ_BN;
+          VQ_ONE {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            // A k-step k: slab k/4 (z_hi|z_hi , z_lo|z_lo), 32 B step inside; B: [e_hi|e_lo] k%4
-            const uint64_t da = umma_desc_sw128(smem_u32(smA + (rh * 2 + (k >> 2)) * VQ_A_SLAB)) + 2 * (k & 3);
-            umma_ss(tacc, da, db + 2 * (k & 3), idesc, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) {
+              // A k-step k: slab k/4 (z_hi|z_hi , z_lo|z_lo), 32 B step inside; B: [e_hi|e_lo] k%4
+              const uint64_t da = umma_desc_sw128(smem_u32(smA + (rh * 2 + (k >> 2)) * VQ_A_SLAB)) + 2 * (k & 3);
+              umma_ss(tacc, da, db + 2 * (k & 3), idesc, k != 0 ? 1u : 0u);
+            }
+            umma_commit(&b_empty[st]);
+            umma_commit(&t_full[as * 2 + rh]);
           }
-          umma_commit(&b_empty[st]);
-          umma_commit(&t_full[as * 2 + rh]);
           if (++st == VQ_BSTAGES) { st = 0; ph ^= 1; }
           if (++as == 2) { as = 0; aph ^= 1; }
         }
