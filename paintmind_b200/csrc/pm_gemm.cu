@@ -166,23 +166,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // =============================== TMA producer =====================================
-    if (lane == 0) {
+    // (service warps run CONVERGED, an elected lane issues TMA / MMA / commit: divergent lane-0 loops cost ~16 instructions of
+    //  uniform-register plumbing per tcgen05.mma — see pm_attn4.cu; -DPM_GEMM_LANE0=1 restores them)
+#ifdef PM_GEMM_LANE0
+#define GEMM_SERVICE_LANES (lane == 0)
+#define GEMM_ONE
+#else
+#define GEMM_SERVICE_LANES true
+#define GEMM_ONE if (elect_one())
+#endif
+    if (GEMM_SERVICE_LANES) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const TileCoord tc = tile_coord(tile, n_tiles, BN, TILE_M, m_off);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (CTA2) {
-            // both CTAs load their own A rows and their half of the W tile; all bytes are credited to the
-            // leader's full barrier, which alone is armed (with the pair's total)
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, tc.m0);
-            tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, tc.n0 + static_cast<int>(rank) * Cfg::B_ROWS);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, tc.m0);
-            tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, tc.n0);
+          GEMM_ONE {
+            if (CTA2) {
+              // both CTAs load their own A rows and their half of the W tile; all bytes are credited to the
+              // leader's full barrier, which alone is armed (with the pair's total)
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, tc.m0);
+              tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, tc.n0 + static_cast<int>(rank) * Cfg::B_ROWS);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, tc.m0);
+              tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, tc.n0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -190,7 +201,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =======================================
-    if (lane == 0 && rank == 0) {        // in a CTA pair only the leader issues MMAs
+    if (GEMM_SERVICE_LANES && rank == 0) {        // in a CTA pair only the leader issues MMAs
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -212,21 +223,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(smA + stage * Cfg::A_BYTES));
           const uint64_t db = umma_desc_sw128(smem_u32(smB + stage * Cfg::B_BYTES));
+          GEMM_ONE {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in 16 B units
-            if (CTA2) umma_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in 16 B units
+              if (CTA2) umma_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+            if (CTA2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+            // accumulator complete -> epilogue (of both CTAs)
+            if (kb == k_blocks - 1) {
+              if (CTA2) umma_commit_2sm(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);
+            }
           }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
-          if (CTA2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete -> epilogue (of both CTAs)
-        if (CTA2) umma_commit_2sm(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      if (p.debug != nullptr) {
+      if (p.debug != nullptr && lane == 0) {
         long long* d = p.debug + 4 * static_cast<size_t>(blockIdx.x);
         d[0] = t_acc; d[1] = t_opr; d[2] = clock64() - t_begin; d[3] = k_blocks;
       }
