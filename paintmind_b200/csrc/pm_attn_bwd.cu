@@ -129,21 +129,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tA1 = tmem_base + 384, tA2 = tmem_base + 448;
 
+  // Service warps run CONVERGED and an elected lane issues TMA / MMA / commit (-DPM_AB_LANE0=1: the old divergent lane-0 loops,
+  // in which every tcgen05.mma costs ~16 instructions of uniform-register plumbing — see pm_attn4.cu)
+#ifdef PM_AB_LANE0
+#define AB_SERVICE_LANES (lane == 0)
+#define AB_ONE
+#else
+#define AB_SERVICE_LANES true
+#define AB_ONE if (elect_one())
+#endif
   if (warp == AB_CW) {
     // ===================================== TMA producer ======================================
-    if (lane == 0) {
+    if (AB_SERVICE_LANES) {
       int g = 0;                                             // running column-tile counter (ring position)
       for (int i = 0; i < my_items; ++i) {
         const AbItem it = ab_item(blockIdx.x + i * gridDim.x, n_rt, p.H);
         const int rs = i & 1;
         mbar_wait_a(r_empty + 8 * rs, ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx_a(r_full + 8 * rs, 2 * AB_TILE);
-        tma_load_3d_a(sR + rs * 2 * AB_TILE, &tmR1, r_full + 8 * rs, it.h * AB_D, it.rt * AB_T, it.b);
-        tma_load_3d_a(sR + rs * 2 * AB_TILE + AB_TILE, &tmR2, r_full + 8 * rs, it.h * AB_D, it.rt * AB_T, it.b);
+        AB_ONE {
+          mbar_arrive_expect_tx_a(r_full + 8 * rs, 2 * AB_TILE);
+          tma_load_3d_a(sR + rs * 2 * AB_TILE, &tmR1, r_full + 8 * rs, it.h * AB_D, it.rt * AB_T, it.b);
+          tma_load_3d_a(sR + rs * 2 * AB_TILE + AB_TILE, &tmR2, r_full + 8 * rs, it.h * AB_D, it.rt * AB_T, it.b);
+        }
         const size_t vec_base = (static_cast<size_t>(it.b) * p.H + it.h) * p.lse_ld;
         for (int t = 0; t < T; ++t, ++g) {
           const int st = g % AB_NST;
           mbar_wait_a(c_empty + 8 * st, ((g / AB_NST) & 1) ^ 1);
+          AB_ONE {
           mbar_arrive_expect_tx_a(c_full + 8 * st, 2 * AB_TILE + (DKV ? 1024 : 0));
           tma_load_3d_a(sC + st * 2 * AB_TILE, &tmC1, c_full + 8 * st, it.h * AB_D, t * AB_T, it.b);
           tma_load_3d_a(sC + st * 2 * AB_TILE + AB_TILE, &tmC2, c_full + 8 * st, it.h * AB_D, t * AB_T, it.b);
@@ -156,12 +168,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                          ::"r"(sVec + st * 1024 + 512), "l"(reinterpret_cast<uint64_t>(p.nds + vec_base + t * AB_T)), "r"(512u), "r"(c_full + 8 * st)
                          : "memory");
           }
+          }
         }
       }
     }
   } else if (warp == AB_CW + 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0 && total_steps > 0) {
+    if (AB_SERVICE_LANES && total_steps > 0) {
       constexpr uint32_t idesc_ss = umma_idesc_bf16(AB_T, AB_T, 0, 0);     // 128 x 128 x 16, both K-major
       constexpr uint32_t idesc_ts = umma_idesc_bf16(AB_T, AB_D, 0, 1);     // A from TMEM, B MN-major
       const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320;
@@ -177,25 +190,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         tc_fence_after();
         const uint64_t dr1 = umma_desc_sw128(sR + rs * 2 * AB_TILE), dr2 = umma_desc_sw128(sR + rs * 2 * AB_TILE + AB_TILE);
         const uint64_t dc1 = umma_desc_sw128(sC + st * 2 * AB_TILE), dc2 = umma_desc_sw128(sC + st * 2 * AB_TILE + AB_TILE);
+        AB_ONE {
 #pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tS, dr1 + 2 * k, dc1 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+          for (int k = 0; k < AB_D / 16; ++k) umma_ss(tS, dr1 + 2 * k, dc1 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k) umma_ss(tDP, dr2 + 2 * k, dc2 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
-        umma_commit_a(s_full);
+          for (int k = 0; k < AB_D / 16; ++k) umma_ss(tDP, dr2 + 2 * k, dc2 + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+          umma_commit_a(s_full);
+        }
       };
       // acc1 (+)= dS' C1 (and acc2 (+)= P' C2): the column operands re-read as MN-major, 128 contraction rows
       auto issue_ts = [&](int g) {
         const int i = g / T, t = g - i * T;
         const int st = g % AB_NST;
         const uint64_t dc1 = umma_desc_sw128(sC + st * 2 * AB_TILE), dc2 = umma_desc_sw128(sC + st * 2 * AB_TILE + AB_TILE);
+        AB_ONE {
 #pragma unroll
-        for (int kk = 0; kk < AB_T / 16; ++kk) {
-          umma_ts(tA1, tDS + 8 * kk, dc1 + kk * (2048 >> 4), idesc_ts, (t | kk) != 0 ? 1u : 0u);
-          if (DKV) umma_ts(tA2, tP + 8 * kk, dc2 + kk * (2048 >> 4), idesc_ts, (t | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < AB_T / 16; ++kk) {
+            umma_ts(tA1, tDS + 8 * kk, dc1 + kk * (2048 >> 4), idesc_ts, (t | kk) != 0 ? 1u : 0u);
+            if (DKV) umma_ts(tA2, tP + 8 * kk, dc2 + kk * (2048 >> 4), idesc_ts, (t | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit_a(acc_done);
+          umma_commit_a(c_empty + 8 * st);
+          if (t == T - 1) umma_commit_a(r_empty + 8 * (i & 1));             // every MMA that read this item's row tiles is done
         }
-        umma_commit_a(acc_done);
-        umma_commit_a(c_empty + 8 * st);
-        if (t == T - 1) umma_commit_a(r_empty + 8 * (i & 1));             // every MMA that read this item's row tiles is done
       };
       issue_ss(0);
       for (int g = 0; g < total_steps; ++g) {
@@ -211,7 +228,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         tc_fence_after();
         issue_ts(g);                                   // this step's accumulation runs underneath the next step's exponentials
       }
-      if (p.debug != nullptr) {
+      if (p.debug != nullptr && lane == 0) {
         long long* d = p.debug + 8 * static_cast<size_t>(blockIdx.x);
         d[0] = w_f; d[1] = w_c; d[2] = w_p; d[3] = clock64() - t_begin;
       }

@@ -73,19 +73,30 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Service warps run CONVERGED and an elected lane issues TMA / MMA / commit (-DPM_WG_LANE0=1: the old divergent lane-0 loops,
+  // in which every tcgen05.mma costs ~16 instructions of uniform-register plumbing — see pm_attn4.cu)
+#ifdef PM_WG_LANE0
+#define WG_SERVICE_LANES (lane == 0)
+#define WG_ONE
+#else
+#define WG_SERVICE_LANES true
+#define WG_ONE if (elect_one())
+#endif
   if (warp == 0) {
-    if (lane == 0) {
+    if (WG_SERVICE_LANES) {
       for (int i = 0; i < nkb; ++i) {
         const int st = i % WG_STAGES;
         mbar_wait_a(empty_bar + 8 * st, ((i / WG_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx_a(full_bar + 8 * st, Cfg::STAGE_BYTES);
-        const int tok = (kb0 + i) * WG_TOK;
-        tma_load_3d_a(sA + st * Cfg::A_BYTES, &tmA, full_bar + 8 * st, 0, tok, n0 / 64);
-        tma_load_3d_a(sB + st * Cfg::B_BYTES, &tmB, full_bar + 8 * st, 0, tok, k0 / 64);
+        WG_ONE {
+          mbar_arrive_expect_tx_a(full_bar + 8 * st, Cfg::STAGE_BYTES);
+          const int tok = (kb0 + i) * WG_TOK;
+          tma_load_3d_a(sA + st * Cfg::A_BYTES, &tmA, full_bar + 8 * st, 0, tok, n0 / 64);
+          tma_load_3d_a(sB + st * Cfg::B_BYTES, &tmB, full_bar + 8 * st, 0, tok, k0 / 64);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nkb > 0) {
+    if (WG_SERVICE_LANES && nkb > 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64 * GB, 1, 1);       // both operands MN-major
       for (int i = 0; i < nkb; ++i) {
         const int st = i % WG_STAGES;
@@ -93,12 +104,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         const uint64_t da = umma_desc_sw128_mn(sA + st * Cfg::A_BYTES, WG_GROUP_BYTES);
         const uint64_t db = umma_desc_sw128_mn(sB + st * Cfg::B_BYTES, WG_GROUP_BYTES);
+        WG_ONE {
 #pragma unroll
-        for (int k = 0; k < WG_TOK / 16; ++k)       // 16 tokens = 2 KB further along the contraction dimension
-          umma_ss(tmem_base, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc, (i | k) != 0 ? 1u : 0u);
-        umma_commit_a(empty_bar + 8 * st);
+          for (int k = 0; k < WG_TOK / 16; ++k)       // 16 tokens = 2 KB further along the contraction dimension
+            umma_ss(tmem_base, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc, (i | k) != 0 ? 1u : 0u);
+          umma_commit_a(empty_bar + 8 * st);
+          if (i == nkb - 1) umma_commit_a(tfull_bar);
+        }
       }
-      umma_commit_a(tfull_bar);
     }
   } else {
     const int q = warp & 3;
