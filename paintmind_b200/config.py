@@ -78,8 +78,18 @@ vit_tiny_test_config = {
     "dec": _vit(64, 8, 128, 2, 2, 256, 64, 0.0, out_channels=3),
 }
 
+# 256-token variant: BASELINE configs[4] is worded "256 tokens" while the reference's only
+# registered pipeline runs 1024 (256 x 256 images, patch 8).  The same two architectures at image_size 128 give 16 x 16 = 256
+# tokens; registered under their own names so that a 256-token number can never be mistaken for the reference configuration.
+vit_s_vqgan_128_config = copy.deepcopy(vit_s_vqgan_config)
+vit_s_vqgan_128_config["enc"]["image_size"] = 128
+vit_s_vqgan_128_config["dec"]["image_size"] = 128
+pipeline_v1_128_config = dict(pipeline_v1_config, stage1="vit-s-vqgan-128")
+
 ver2cfg = {
     "vit-s-vqgan": vit_s_vqgan_config,
     "paintmindv1": pipeline_v1_config,
     "vit-tiny-test": vit_tiny_test_config,
+    "vit-s-vqgan-128": vit_s_vqgan_128_config,
+    "paintmindv1-128": pipeline_v1_128_config,
 }

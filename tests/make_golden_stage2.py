@@ -36,17 +36,27 @@ def stage2_fixtures(pm):
     np.savez_compressed(GOLD / "stage2_tiny.npz", **out)
     print("stage2_tiny:", {k: v.shape for k, v in out.items()})
 
-    # ---- full-size pipeline, one MaskGIT step with injected noise ----
+    step_fixture(pm, "paintmindv1", "stage2_step.npz")
+    # the 256-token variant (image_size 128, registered in THIS repo's config.py only): the reference classes take every size from
+    # the config, so its registry gets the two entries for the duration of this script (in memory; /root/reference is untouched)
+    import paintmind.config as RC
+    RC.ver2cfg["vit-s-vqgan-128"] = ver2cfg["vit-s-vqgan-128"]
+    RC.ver2cfg["paintmindv1-128"] = ver2cfg["paintmindv1-128"]
+    step_fixture(pm, "paintmindv1-128", "stage2_step_256.npz")
+
+
+def step_fixture(pm, version, out_name):
+    """One MaskGIT step of the reference Pipeline with injected noise (generate.py:159-181)."""
     import paintmind.generate as G
-    cfg1 = ver2cfg["vit-s-vqgan"]
-    cfg2 = ver2cfg["paintmindv1"]
-    pipe = pm.create_model(arch="pipeline", version="paintmindv1", pretrained=False).eval()
+    cfg2 = ver2cfg[version]
+    cfg1 = ver2cfg[cfg2["stage1"]]
+    pipe = pm.create_model(arch="pipeline", version=version, pretrained=False).eval()
     sd = {("vqgan." + k): v for k, v in synthetic.make_vqgan_state_dict(cfg1, seed=0).items()}
     sd.update(synthetic.make_stage2_state_dict(cfg2, cfg1, seed=1, context_dim=1024))
     res = pipe.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
-    B, N, V = 1, 1024, 8192
-    text, ids, u = full_step_inputs()
+    N, V = (cfg1["enc"]["image_size"] // cfg1["enc"]["patch_size"]) ** 2, cfg1["n_embed"]
+    text, ids, u = full_step_inputs(N=N)
     orig = G.gumbel_noise
     G.gumbel_noise = lambda t: -G.log(-G.log(u))
     try:
@@ -64,7 +74,7 @@ def stage2_fixtures(pm):
     top6 = logits.topk(6, dim=-1)
     k = max(int((mask_ratio * N).item()), 1)
     np.savez_compressed(
-        GOLD / "stage2_step.npz",
+        GOLD / out_name,
         ids_in=ids.numpy().astype(np.int16), mask_ratio=float(mask_ratio), k=k,
         tokens_head=tokens[0, :8].numpy().astype(np.float32),
         logits_sub=logits[0, ::16, ::16].numpy().astype(np.float32),
@@ -75,5 +85,5 @@ def stage2_fixtures(pm):
         img_sub=img[0, :, ::4, ::4].numpy().astype(np.float32),
         text_sum=float(text.double().sum()), u_sum=float(u.double().sum()),
     )
-    print(f"stage2_step: k={k} masked_in={(ids == V).sum().item()} masked_out={(new_ids == V).sum().item()} "
+    print(f"{out_name}: N={N} k={k} masked_in={(ids == V).sum().item()} masked_out={(new_ids == V).sum().item()} "
           f"logits absmax={logits.abs().max():.3f}")

@@ -118,23 +118,49 @@ def test_cond_transformer_tiny_vs_reference_golden(cuda_device):
             assert err.max() < 0.06 and err.mean() < 0.01
 
 
-@pytest.fixture(scope="module")
-def full_pipeline(cuda_device):
+def _make_pipeline(version, dev):
     import paintmind_b200 as pm
-    cfg1, cfg2 = ver2cfg["vit-s-vqgan"], ver2cfg["paintmindv1"]
-    pipe = pm.create_model(arch="pipeline", version="paintmindv1", pretrained=False)
+    cfg2 = ver2cfg[version]
+    cfg1 = ver2cfg[cfg2["stage1"]]
+    pipe = pm.create_model(arch="pipeline", version=version, pretrained=False)
     sd = {("vqgan." + k): v for k, v in synthetic.make_vqgan_state_dict(cfg1, seed=0).items()}
     sd.update(synthetic.make_stage2_state_dict(cfg2, cfg1, seed=1, context_dim=1024))
     res = pipe.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
-    return pipe.to(cuda_device).eval()
+    return pipe.to(dev).eval()
+
+
+@pytest.fixture(scope="module")
+def full_pipeline(cuda_device):
+    return _make_pipeline("paintmindv1", cuda_device)
 
 
 def test_pipeline_sample_step_vs_reference_golden(cuda_device, full_pipeline):
-    g = load_golden("stage2_step.npz")
-    pipe = full_pipeline
-    dev = cuda_device
-    text, ids, u = full_step_inputs()
+    _check_sample_step(full_pipeline, load_golden("stage2_step.npz"), cuda_device)
+
+
+def test_pipeline_256_token_variant_vs_reference_golden(cuda_device):
+    """The labelled 256-token configuration ("paintmindv1-128": image_size 128, SURVEY.md F5 / BASELINE configs[4]'s wording):
+    one MaskGIT step against the unmodified reference classes run at that size, same criteria as the 1024-token step, and a
+    generate() through the whole-step CUDA graph."""
+    pipe = _make_pipeline("paintmindv1-128", cuda_device)
+    assert pipe.num_tokens == 256
+    _check_sample_step(pipe, load_golden("stage2_step_256.npz"), cuda_device)
+    outs = []
+    for mode in (False, True):
+        pipe.cuda_graph = mode
+        torch.manual_seed(3)
+        text = torch.randn(2, 77, 1024, generator=torch.Generator().manual_seed(4)).to(cuda_device)
+        outs.append(pipe.generate(text, timesteps=4, temperature=1.0, topk=5, save_interval=2))
+    pipe.cuda_graph = None
+    assert len(outs[0]) == len(outs[1]) == 2
+    for a, b in zip(*outs):
+        assert tuple(a.shape) == (2, 3, 128, 128) and torch.equal(a, b)
+
+
+def _check_sample_step(pipe, g, dev):
+    N = pipe.num_tokens
+    text, ids, u = full_step_inputs(N=N)
     text, ids, u = text.to(dev), ids.to(dev), u.to(dev)
     tokens = pipe.ids2tokens(ids)
     np.testing.assert_array_equal(tokens[0, :8].cpu().numpy(), g["tokens_head"])
@@ -147,7 +173,7 @@ def test_pipeline_sample_step_vs_reference_golden(cuda_device, full_pipeline):
     new_ids, img = pipe.sample(ids, float(g["mask_ratio"]), text=text, topk=5, temperature=0.75, _noise=u)
     k = int(g["k"])
     assert int((new_ids == 8192).sum()) == k
-    assert img.shape == (1, 3, 256, 256) and img.dtype == torch.float32
+    assert img.shape == (1, 3, pipe.image_size, pipe.image_size) and img.dtype == torch.float32
     # (1) the tail is exact given OUR logits
     pred_r, ids_r, scores_r = ref_tail(pipe._last_logits, ids, u, 5, 0.75, 8192, k)
     assert torch.equal(pipe._last_pred_ids, pred_r)

@@ -1,5 +1,6 @@
 """Numpy oracle of the stage-2 path against the reference's golden outputs (CPU)."""
 import numpy as np
+import pytest
 import torch
 
 from conftest import load_golden
@@ -21,12 +22,16 @@ def test_oracle_cond_transformer_tiny():
             np.testing.assert_allclose(O.cond_transformer_forward(tokens.numpy(), None, sd, TINY2), g["logits_nocontext"], atol=2e-4, rtol=0)
 
 
-def test_oracle_maskgit_step_full_size():
-    g = load_golden("stage2_step.npz")
-    cfg1, cfg2 = ver2cfg["vit-s-vqgan"], ver2cfg["paintmindv1"]
+@pytest.mark.parametrize("version,fixture", [("paintmindv1", "stage2_step.npz"), ("paintmindv1-128", "stage2_step_256.npz")])
+def test_oracle_maskgit_step_full_size(version, fixture):
+    """1024 tokens (the reference's registered pipeline) and the labelled 256-token variant (image_size 128)."""
+    g = load_golden(fixture)
+    cfg2 = ver2cfg[version]
+    cfg1 = ver2cfg[cfg2["stage1"]]
+    N = (cfg1["enc"]["image_size"] // cfg1["enc"]["patch_size"]) ** 2
     sd = {("vqgan." + k): v.numpy() for k, v in synthetic.make_vqgan_state_dict(cfg1, seed=0).items()}
     sd.update({k: v.numpy() for k, v in synthetic.make_stage2_state_dict(cfg2, cfg1, seed=1, context_dim=1024).items()})
-    text, ids, u = full_step_inputs()
+    text, ids, u = full_step_inputs(N=N)
     assert abs(float(text.double().sum()) - float(g["text_sum"])) < 1e-6 and abs(float(u.double().sum()) - float(g["u_sum"])) < 1e-3
     np.testing.assert_array_equal(ids.numpy(), g["ids_in"].astype(np.int64))
     new_ids, img, pred, logits, scores, k = O.sample_step(ids.numpy(), float(g["mask_ratio"]), text.numpy(), 5, 0.75, u.numpy(), sd, cfg2, cfg1)
