@@ -142,8 +142,23 @@ __device__ __forceinline__ void a4_exps(const uint32_t (&s)[2][32], float delta,
   }
 }
 
+// the same for 32 keys (the split fast path below)
+template <int EMU>
+__device__ __forceinline__ void a4_exps32(const uint32_t (&s)[32], float2& la, float2& lb, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    const float2 a = make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+    const bool poly = ((e >> 1) & 3) < EMU;
+    const float2 ex = poly ? a4_exp2_poly2(a) : make_float2(a4_ex2(a.x), a4_ex2(a.y));
+    if ((e >> 1) & 1) lb = __fadd2_rn(lb, ex);
+    else la = __fadd2_rn(la, ex);
+    pk[e >> 1] = pack_bf16x2(ex.x, ex.y);
+  }
+}
+
 // TRAIN : also emit the row log-sum-exp (base 2, of the pre-scaled logits) and an fp32 copy of the output (training forward)
-template <int EMU, bool TRAIN>
+// SPLIT : 1 = the steady-state step loads and exponentiates its 64 scores as two halves of 32 (see the fast path)
+template <int EMU, bool TRAIN, int SPLIT>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
@@ -369,8 +384,12 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const uint32_t tS_oth = tmem_base + t * 128 + (kh ^ 1) * 64 + lane_off;
     const uint32_t tP = tmem_base + 256 + t * 64 + kh * 32 + lane_off;
     const uint32_t tO = tmem_base + 384 + t * 64 + lane_off;
-    const uint32_t b_s_full = s_full + 8 * t, b_s_free = s_free + 8 * t;
-    const uint32_t b_p_full = p_full + 16 * t + 8 * kh, b_pv_done = pv_done + 8 * t;
+    // Two opaque base registers for the four barriers of the hot loop: left to itself ptxas re-derives each address from %tid and
+    // %cluster_ctaid (two S2R, ~25 cycles each) in front of the waits and arrivals of every step.
+    uint32_t bar_t = s_full + 8 * t, bar_p = p_full + 16 * t + 8 * kh;
+    asm volatile("" : "+r"(bar_t), "+r"(bar_p));
+    const uint32_t b_s_full = bar_t, b_s_free = bar_t + (s_free - s_full);
+    const uint32_t b_p_full = bar_p, b_pv_done = bar_t + (pv_done - s_full);
     const uint32_t a_row = sA + t * A4_BIAS_BYTES + row_in_tile * 16;      // this row's (-m, 1) word (written by the kh = 0 thread)
     uint8_t* const stg = smO + t * A4_TILE_BYTES + row_in_tile * 128;
     float* const l_mine = smL + (t * 2 + kh) * 128 + row_in_tile;
@@ -480,10 +499,26 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             a4_exps<true, EMU>(s, m_tile - m_used, la, lb, pk);
           } else {
             // ---- fast pass, tiles 1..: the scores arrive as s - m_used; load, exponentiate, store ----
-            tmem_ld_x32(tS_own, s[0]);
-            tmem_ld_x32(tS_own + 32, s[1]);
-            tmem_ld_wait();
-            tc_fence_before();
+            if (SPLIT) {
+              // Two halves of 32 keys: at most 32 scores + 16 packed words are live instead of 64 + 32.  With all 64 scores in
+              // registers the loop does not fit 104 registers: ptxas kept the step counter in LOCAL memory (four LDL and one STL per
+              // step, ncu: 4.5 M local loads per launch) and rebuilt every barrier address from %tid / %cluster_ctaid in front of
+              // each wait and arrive — on the serial part of the step.  The second load's address depends on the first half's sums
+              // (0 unless NaN), otherwise ptxas hoists it above them and the 64 registers are back.
+              tmem_ld_x32(tS_own, s[0]);
+              tmem_ld_wait();
+              a4_exps32<EMU>(s[0], la, lb, pk[0]);
+              const float chk = (la.x + la.y) + (lb.x + lb.y);
+              const uint32_t dep2 = (chk != chk) ? 1u : 0u;
+              tmem_ld_x32(tS_own + 32 + dep2, s[1]);
+              tmem_ld_wait();
+              tc_fence_before();
+            } else {
+              tmem_ld_x32(tS_own, s[0]);
+              tmem_ld_x32(tS_own + 32, s[1]);
+              tmem_ld_wait();
+              tc_fence_before();
+            }
             if (j == n_kv - 1) {
               // last tile of the item: the next item's first tile must be issued with offset 0 (see above)
               if (m_baked != 0.0f) {
@@ -500,7 +535,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(b_s_free) : "memory");
             }
             ok_pv = mbar_try_wait_a(b_pv_done, (g - 1) & 1);          // poll issued now, consumed after the exponentials
-            a4_exps<false, EMU>(s, 0.0f, la, lb, pk);
+            if (SPLIT) a4_exps32<EMU>(s[1], la, lb, pk[1]);
+            else a4_exps<false, EMU>(s, 0.0f, la, lb, pk);
           }
           if (j > 0 && !ok_pv) mbar_wait_a(b_pv_done, (g - 1) & 1);   // P_t V of the previous step reads the P columns until this fires
           tc_fence_after();
@@ -585,14 +621,17 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 using Attn4KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
 
 struct Attn4Variant {
-  int emu;
+  int emu, split;
   Attn4KernelFn fn;
 };
-// The first entry is the default; PM_ATTN4_VARIANT="emu" picks another one (tuning aid, same function).
+// The first entry is the default; PM_ATTN4_VARIANT="emu" / PM_ATTN4_SPLIT=0|1 pick another one (tuning aid, same function).
 static const Attn4Variant kAttn4Variants[] = {
-    {1, attn4_kernel<1, false>},
-    {0, attn4_kernel<0, false>},
-    {2, attn4_kernel<2, false>},
+    {1, 1, attn4_kernel<1, false, 1>},
+    {1, 0, attn4_kernel<1, false, 0>},
+    {0, 0, attn4_kernel<0, false, 0>},
+    {2, 0, attn4_kernel<2, false, 0>},
+    {0, 1, attn4_kernel<0, false, 1>},
+    {2, 1, attn4_kernel<2, false, 1>},
 };
 
 bool pm_attn4_supported(const AttnParams& p) {
@@ -615,11 +654,13 @@ int pm_attn4_launch(const AttnParams& p, cudaStream_t stream) {
   if (fn == nullptr) {
     const Attn4Variant* v = &kAttn4Variants[0];
     const char* env = getenv("PM_ATTN4_VARIANT");
-    if (env != nullptr) {
-      const int e = atoi(env);
+    const char* env_s = getenv("PM_ATTN4_SPLIT");
+    if (env != nullptr || env_s != nullptr) {
+      const int e = env != nullptr ? atoi(env) : v->emu;
+      const int sp = env_s != nullptr ? atoi(env_s) : v->split;
       v = nullptr;
       for (const Attn4Variant& c : kAttn4Variants)
-        if (c.emu == e) v = &c;
+        if (c.emu == e && c.split == sp) v = &c;
       if (v == nullptr) return PM_ERR_INVALID;
     }
     fn = v->fn;
@@ -627,7 +668,7 @@ int pm_attn4_launch(const AttnParams& p, cudaStream_t stream) {
   static bool attr_done[PM_MAX_DEVICES] = {}, attr_done_train[PM_MAX_DEVICES] = {};
   Attn4KernelFn kern = fn;
   if (p.lse != nullptr || p.o32 != nullptr) {
-    kern = attn4_kernel<1, true>;          // (a separate instantiation: the inference kernel's register allocation is untouched)
+    kern = attn4_kernel<1, true, 1>;   // (a separate instantiation: the inference kernel's register allocation is untouched)
     if ((rc = pm_ensure_dyn_smem(kern, A4_SMEM_BYTES, attr_done_train)) != 0) return rc;
   } else if ((rc = pm_ensure_dyn_smem(fn, A4_SMEM_BYTES, attr_done)) != 0) {
     return rc;
