@@ -380,9 +380,12 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const int q = warp & 3;                        // TMEM lane quarter
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS_own = tmem_base + t * 128 + kh * 64 + lane_off;
+    // (opaque, like the barrier bases below: ptxas otherwise re-derives these per-thread constants from %tid — S2R, five dependent
+    //  integer operations, R2UR — in front of the score load and of the P store of every step)
+    uint32_t tS_own = tmem_base + t * 128 + kh * 64 + lane_off;
+    uint32_t tP = tmem_base + 256 + t * 64 + kh * 32 + lane_off;
+    asm volatile("" : "+r"(tS_own), "+r"(tP));
     const uint32_t tS_oth = tmem_base + t * 128 + (kh ^ 1) * 64 + lane_off;
-    const uint32_t tP = tmem_base + 256 + t * 64 + kh * 32 + lane_off;
     const uint32_t tO = tmem_base + 384 + t * 64 + lane_off;
     // Two opaque base registers for the four barriers of the hot loop: left to itself ptxas re-derives each address from %tid and
     // %cluster_ctaid (two S2R, ~25 cycles each) in front of the waits and arrivals of every step.
