@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpaintmind_b200.so"
+import os
+
+# PM_B200_LIB: another build of the same library (same-box A/B of two builds, e.g. scripts/abwd_opaque_ab.sh); default: the in-tree one
+_LIB_PATH = Path(os.environ.get("PM_B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libpaintmind_b200.so"))
 _lib = None
 
 PM_OUT_BF16, PM_OUT_F32, PM_OUT_UNPATCH, PM_OUT_UNPATCH_U8 = 0, 1, 2, 3

@@ -239,8 +239,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const int q = warp & 3;                                   // TMEM lane quarter
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tSg = tmem_base + gq * AB_COLS + lane_off, tDPg = tSg + 128;
-    const uint32_t tPg = tmem_base + 256 + gq * (AB_COLS / 2) + lane_off, tDSg = tPg + 64;
+    // per-thread constants of the step loop, opaque to the optimiser: ptxas otherwise re-derives them from %tid / %cluster_ctaid
+    // (S2R + a chain of integer operations + R2UR) in front of the loads, waits, stores and arrivals of every step (see pm_attn4.cu)
+    uint32_t tSg_o = tmem_base + gq * AB_COLS + lane_off, tPg_o = tmem_base + 256 + gq * (AB_COLS / 2) + lane_off, bar_o = s_full;
+#ifndef PM_ABWD_PLAIN
+    asm volatile("" : "+r"(tSg_o), "+r"(tPg_o), "+r"(bar_o));
+#endif
+    const uint32_t tSg = tSg_o, tDPg = tSg + 128;
+    const uint32_t tPg = tPg_o, tDSg = tPg + 64;
+    const uint32_t s_full = bar_o, p_full = bar_o + 8, acc_done = bar_o + 16, s_free = bar_o + 24, c_full = bar_o - 16 * AB_NST;
     const float2 c2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
     AB_TIMER(long long w_s = 0, w_a = 0, c_math = 0, c_epi = 0;)
     int g = 0;
