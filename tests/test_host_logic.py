@@ -106,6 +106,20 @@ def test_pipeline_surface_and_schedule():
     assert isinstance(mask_schedule(0.5), np.floating)
 
 
+def test_256_token_variant_is_registered_under_its_own_name():
+    """a 256-token number must come from an explicitly registered image_size-128 configuration; the reference's two
+    names keep the reference's values (1024 tokens)."""
+    from paintmind_b200.config import ver2cfg
+    v1, v128 = ver2cfg["vit-s-vqgan"], ver2cfg["vit-s-vqgan-128"]
+    assert v1["enc"]["image_size"] == v1["dec"]["image_size"] == 256
+    assert v128["enc"]["image_size"] == v128["dec"]["image_size"] == 128
+    assert {k: v for k, v in v128["enc"].items() if k != "image_size"} == {k: v for k, v in v1["enc"].items() if k != "image_size"}
+    assert (v128["enc"]["image_size"] // v128["enc"]["patch_size"]) ** 2 == 256
+    p1, p128 = ver2cfg["paintmindv1"], ver2cfg["paintmindv1-128"]
+    assert p1["stage1"] == "vit-s-vqgan" and p128["stage1"] == "vit-s-vqgan-128"
+    assert {k: v for k, v in p128.items() if k != "stage1"} == {k: v for k, v in p1.items() if k != "stage1"}
+
+
 def test_training_forward_has_no_cpu_fallback():
     """VQModel.forward under autograd (the generator training step) on a CPU model must fail loudly, like the inference path."""
     import pytest
