@@ -19,7 +19,9 @@
 // Every query row is shared by two threads (same TMEM lane, warps w and w + 4), each owning 64 of the tile's 128 keys.
 //   * first key tile of an item (and every tile of the exact pass): both threads reduce all 128 scores (bitwise the same
 //     maximum, no exchange); the kh = 0 thread writes the row's (-m, 1) word of A_t before S_t is handed back;
-//   * later tiles: tcgen05.ld of the own 64 scores, exp2, row sums, bf16 P into the own 32 P columns — nothing else;
+//   * later tiles: tcgen05.ld of the own 64 scores (as two halves of 32, so that the step fits its 104 registers without local
+//     memory), exp2, row sums, bf16 P into the own 32 P columns — nothing else; the loop's barrier / TMEM addresses are kept in
+//     registers (opaque to ptxas, which otherwise re-derives them from %tid in front of every wait, load, store and arrival);
 //   * P_t V is issued in two halves; row sums meet once per item in shared memory; each thread stores 32 output columns.
 // 640 threads: warps 0-15 softmax, 16 TMA producer, 17 / 18 MMA issuers.  Registers 104 / 64 after setmaxnreg (640 x 96 pool).
 // TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
