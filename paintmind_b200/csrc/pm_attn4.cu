@@ -74,6 +74,9 @@ __device__ __forceinline__ float a4_bf16_round(float x) { return __bfloat162floa
 // ahead and is latency-insensitive: it sleeps PM_A4_PROD_SLEEP ns after a failed poll (0.7603 -> 0.7565 ms sustained with 200,
 // 0.7587 with 1000).  The same idea on the MMA issuers (a nanosleep between issuing a step and polling for the next) is a loss:
 // 300 ns in the P.V issuer 0.786 ms, 700 ns 0.880 ms — their wake-up latency is on the critical path (profiles/r02_attention.md).
+#ifndef PM_A4_LD2_AT
+#define PM_A4_LD2_AT 24
+#endif
 #ifndef PM_A4_PROD_SLEEP
 #define PM_A4_PROD_SLEEP 200
 #endif
@@ -144,11 +147,11 @@ __device__ __forceinline__ void a4_exps(const uint32_t (&s)[2][32], float delta,
   }
 }
 
-// the same for 32 keys (the split fast path below)
-template <int EMU>
+// the same for 32 keys (the split fast path below), elements [E0, E1)
+template <int EMU, int E0 = 0, int E1 = 32>
 __device__ __forceinline__ void a4_exps32(const uint32_t (&s)[32], float2& la, float2& lb, uint32_t (&pk)[16]) {
 #pragma unroll
-  for (int e = 0; e < 32; e += 2) {
+  for (int e = E0; e < E1; e += 2) {
     const float2 a = make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1]));
     const bool poly = ((e >> 1) & 3) < EMU;
     const float2 ex = poly ? a4_exp2_poly2(a) : make_float2(a4_ex2(a.x), a4_ex2(a.y));
@@ -512,10 +515,13 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
               // (0 unless NaN), otherwise ptxas hoists it above them and the 64 registers are back.
               tmem_ld_x32(tS_own, s[0]);
               tmem_ld_wait();
-              a4_exps32<EMU>(s[0], la, lb, pk[0]);
+              // the second load is issued when PM_A4_LD2_AT of the 32 first-half scores are done: its latency hides under the rest
+              // (24: 0.611 -> 0.606 ms against issuing it after all 32)
+              a4_exps32<EMU, 0, PM_A4_LD2_AT>(s[0], la, lb, pk[0]);
               const float chk = (la.x + la.y) + (lb.x + lb.y);
               const uint32_t dep2 = (chk != chk) ? 1u : 0u;
               tmem_ld_x32(tS_own + 32 + dep2, s[1]);
+              a4_exps32<EMU, PM_A4_LD2_AT, 32>(s[0], la, lb, pk[0]);
               tmem_ld_wait();
               tc_fence_before();
             } else {
