@@ -1,5 +1,5 @@
 # A/B of the fast-path forms of pm_attn4 (PM_ATTN4_SPLIT = 0: all 64 scores at once; 1: two halves of 32, no local-memory traffic;
-# 2: 1 + next step's first half loaded before the P store): isolated (burst + parity, attn3_ab.py) and inside the timed step of bench.py;
+# (2 = 1 + next step's first half loaded before the P store: measured, a loss, removed): isolated (burst + parity, attn3_ab.py) and inside the timed step of bench.py;
 # alternating order, one box.  usage: bash scripts/attn4_split_ab.sh "1 2 1 2"
 LIST=${1:-"0 1 0 1"}
 for s in $LIST; do
